@@ -1,0 +1,64 @@
+"""ctypes binding of libclearcam_b200.so (C-ABI declared in include/clearcam_b200.h).
+
+The product path has NO fallback: if the shared library is missing or a call fails, a CCError is raised
+(the reference's callers catch exceptions and supervise restarts themselves, clearcam.py:543-546).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libclearcam_b200.so")
+
+
+class CCError(RuntimeError):
+    pass
+
+
+_lib = None
+
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+_SIGS = {
+    "cc_version": (_i, []),
+    "cc_last_error": (ctypes.c_char_p, []),
+    "cc_device_check": (_i, []),
+    "cc_conv2d": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp]),
+}
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raises CCError when the library was not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CCError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)")
+        h = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(h, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = h
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().cc_last_error()
+        raise CCError(f"{what} failed ({rc}): {msg.decode() if msg else '?'}")
+
+
+def declared_symbols():
+    return sorted(_SIGS)
+
+
+def ptr(t):
+    """Device/host pointer of a torch tensor (or None)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr(stream=None):
+    import torch
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return ctypes.c_void_p(s.cuda_stream)

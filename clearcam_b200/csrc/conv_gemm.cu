@@ -1,0 +1,429 @@
+// Implicit-GEMM conv / linear on tcgen05 (sm_100a). See conv_gemm.cuh for what it replaces in the reference.
+//
+// GEMM view: M = output pixels (N*H*W), N = Cout, K = kh*kw*Cin.
+//   * CTA tile: 128 pixels x BN channels; the 128 pixels are a TW x TH x TN box of the NHWC output
+//     (TW*TH*TN = 128, chosen per layer so 20x20/40x40 maps tile without waste).
+//   * K loop: for each filter tap (r,s) and each BK-channel chunk, ONE TMA box load of the input shifted by
+//     the tap offset (TMA zero-fills out-of-bounds = conv padding) + one TMA box of the weights.
+//     stride 2 uses a 5-D "pixel pair" view (dims: 2*C, W/2, 2, H/2, N) so every tap is again a dense box.
+//   * smem tiles are K-major, 128/64/32-byte swizzled (BK = 64/32/16 channels) exactly as TMA writes them;
+//     tcgen05.mma (M=128, N=BN, K=16) reads them through shared-memory descriptors; accumulators live in TMEM
+//     (2 x 256 columns, double buffered so the epilogue of tile i overlaps the mainloop of tile i+1).
+//   * warp roles: w0 = TMA producer, w1 = MMA issuer, w2 = TMEM allocator, w4..7 = epilogue
+//     (tcgen05.ld -> bias -> SiLU/GELU -> (+residual) -> bf16/fp32 -> padded smem staging -> coalesced 16-B stores).
+//   * persistent: grid = min(tiles, SMs), static round-robin tile schedule.
+#include "conv_gemm.cuh"
+#include "cc_common.h"
+#include "cc_ptx.cuh"
+#include <string.h>
+
+namespace cc {
+
+static constexpr int kThreads = 256;
+static constexpr int kTileM = 128;
+static constexpr uint32_t kTmemCols = 512;
+static constexpr int kMaxSmem = 232448;  // 227 KB
+
+__device__ __forceinline__ float act_apply(float x, int act) {
+  if (act == ACT_SILU) {
+    return __fdividef(x, 1.0f + __expf(-x));
+  } else if (act == ACT_GELU_TANH) {
+    // 0.5x(1+tanh(sqrt(2/pi)(x+0.044715x^3))), tanh(u) = 1 - 2/(1+exp(2u))   (models/objects.py:125 gelu())
+    const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+    const float t = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * u));
+    return 0.5f * x * (1.0f + t);
+  }
+  return x;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-B alignment for the 128B-swizzled tiles
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const uint32_t row_bytes = p.BK * 2;
+  const uint32_t a_bytes = kTileM * row_bytes;
+  const uint32_t b_bytes = p.BN * row_bytes;
+  const int S = p.stages;
+  const int es = p.out_f32 ? 4 : 2;
+  const int CH = p.out_f32 ? (p.BN < 64 ? p.BN : 64) : (p.BN < 128 ? p.BN : 128);  // columns per staging pass
+  const uint32_t pitch = CH * es + 16;
+
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + S * a_bytes;
+  uint8_t* sStage = sB + S * b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + ((kTileM * pitch + 15) & ~15u));
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + S;
+  uint64_t* tfull_bar = bars + 2 * S;
+  uint64_t* tempty_bar = bars + 2 * S + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_kb = p.num_taps * p.chunks_per_tap;
+  const int tiles_wh = p.tiles_w * p.tiles_h;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int nb = tile % p.n_blocks;
+        const int m = tile / p.n_blocks;
+        const int w0 = (m % p.tiles_w) << p.lTW;
+        const int h0 = ((m / p.tiles_w) % p.tiles_h) << p.lTH;
+        const int n0 = (m / tiles_wh) << p.lTN;
+        int kb = 0;
+        for (int t = 0; t < p.num_taps; ++t) {
+          const int c_base = p.tap[t][0];
+          const int c1 = w0 + p.tap[t][1];
+          const int c2 = p.s2 ? p.tap[t][2] : h0 + p.tap[t][2];
+          const int c3 = p.s2 ? h0 + p.tap[t][3] : n0;
+          const int c4 = p.s2 ? n0 : 0;
+          for (int ch = 0; ch < p.chunks_per_tap; ++ch, ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+            tma_load_5d(sA + stage * a_bytes, &p.tmA, &full_bar[stage], c_base + ch * p.BK, c1, c2, c3, c4);
+            tma_load_2d(sB + stage * b_bytes, &p.tmB, &full_bar[stage], kb * p.BK, nb * p.BN);
+            if (++stage == S) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      const uint32_t idesc = umma_idesc_f16(kTileM, p.BN, p.ab_fmt);
+      const int kpb = p.BK / 16;  // UMMA_K = 16 for 16-bit inputs
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_smem_desc(smem_u32(sA + stage * a_bytes), row_bytes);
+          const uint64_t bdesc = umma_smem_desc(smem_u32(sB + stage * b_bytes), row_bytes);
+          for (int k = 0; k < kpb; ++k) {
+            // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in the (addr>>4) field
+            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs have read it
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (4 warps, thread == output row) =====================
+    const int ew = warp & 3;              // TMEM lane quarter this warp may access
+    const int row = ew * 32 + lane;       // row of the 128-pixel tile
+    const int et = threadIdx.x - 128;     // 0..127
+    const int TWm = (1 << p.lTW) - 1, THm = (1 << p.lTH) - 1;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int nb = tile % p.n_blocks;
+      const int m = tile / p.n_blocks;
+      const int w0 = (m % p.tiles_w) << p.lTW;
+      const int h0 = ((m / p.tiles_w) % p.tiles_h) << p.lTH;
+      const int n0 = (m / tiles_wh) << p.lTN;
+
+      // this thread's pixel (register phase: residual read)
+      const int pw = w0 + (row & TWm), ph = h0 + ((row >> p.lTW) & THm), pn = n0 + (row >> (p.lTW + p.lTH));
+      const bool pvalid = (pw < p.W) && (ph < p.H) && (pn < p.N);
+      const long long ppix = (static_cast<long long>(pn) * p.H + ph) * p.W + pw;
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + acc * 256 + (static_cast<uint32_t>(ew * 32) << 16);
+
+      for (int cc0 = 0; cc0 < p.BN; cc0 += CH) {
+        const int chn = (p.BN - cc0) < CH ? (p.BN - cc0) : CH;  // columns in this pass (multiple of 16)
+        named_bar_sync(1, 128);                                   // staging buffer free
+        for (int c = 0; c < chn; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(t_row + cc0 + c, v);
+          tmem_ld_wait();
+          const int gcol = nb * p.BN + cc0 + c;  // global output channel of v[0]
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float x = __uint_as_float(v[j]);
+            if (p.bias) x += __ldg(p.bias + gcol + j);
+            f[j] = act_apply(x, p.act);
+          }
+          if (p.res != nullptr && pvalid) {
+            if (p.out_f32) {
+              const float4* r4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) +
+                                                                 ppix * p.res_cs + p.res_co + gcol);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 r = __ldg(r4 + j);
+                f[4 * j + 0] += r.x; f[4 * j + 1] += r.y; f[4 * j + 2] += r.z; f[4 * j + 3] += r.w;
+              }
+            } else {
+              const uint4* r4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res) +
+                                                               ppix * p.res_cs + p.res_co + gcol);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const uint4 r = __ldg(r4 + j);
+                const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&rr[q]);
+                  f[8 * j + 2 * q + 0] += __bfloat162float(h.x);
+                  f[8 * j + 2 * q + 1] += __bfloat162float(h.y);
+                }
+              }
+            }
+          }
+          uint8_t* dst = sStage + row * pitch + c * es;
+          if (p.out_f32) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<float4*>(dst + 16 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              *reinterpret_cast<uint4*>(dst + 16 * j) =
+                  make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                             pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+          }
+        }
+        if (cc0 + CH >= p.BN) {
+          // all TMEM reads of this accumulator done -> hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&tempty_bar[acc]);
+        }
+        named_bar_sync(1, 128);  // staging filled
+        // coalesced copy-out: consecutive threads write consecutive 16-B chunks of a pixel's channel run
+        const int cpr = (chn * es) >> 4;  // 16-B chunks per row
+        const int total = kTileM * cpr;
+        for (int i = et; i < total; i += 128) {
+          const int r = i / cpr;
+          const int chk = i - r * cpr;
+          const int qw = w0 + (r & TWm), qh = h0 + ((r >> p.lTW) & THm), qn = n0 + (r >> (p.lTW + p.lTH));
+          if (qw < p.W && qh < p.H && qn < p.N) {
+            const long long pix = (static_cast<long long>(qn) * p.H + qh) * p.W + qw;
+            const uint4 val = *reinterpret_cast<const uint4*>(sStage + r * pitch + chk * 16);
+            uint8_t* g = reinterpret_cast<uint8_t*>(p.out) +
+                         (pix * p.out_cs + p.out_co + nb * p.BN + cc0) * es + chk * 16;
+            *reinterpret_cast<uint4*>(g) = val;
+          }
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+
+static int ilog2(int x) {
+  int l = 0;
+  while ((1 << l) < x) ++l;
+  return l;
+}
+
+bool conv_gemm_supported(const ConvDesc& d) {
+  if (d.Cin % 16 != 0 || d.Cout % 16 != 0) return false;
+  if (!(d.k == 1 || d.k == 3)) return false;
+  if (!(d.stride == 1 || d.stride == 2)) return false;
+  if (d.stride == 2 && (d.k != 3 || (d.Hin & 1) || (d.Win & 1))) return false;
+  if (d.in_co % 8 != 0 || d.in_cs % 8 != 0) return false;
+  return true;
+}
+
+int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
+  CC_REQUIRE(conv_gemm_supported(d), "conv_gemm: unsupported shape Cin=%d Cout=%d k=%d s=%d Hin=%d Win=%d", d.Cin, d.Cout,
+             d.k, d.stride, d.Hin, d.Win);
+  PFN_encodeTiled enc = get_encode_tiled();
+  CC_REQUIRE(enc != nullptr, "conv_gemm: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  const int es = d.out_f32 ? 4 : 2;
+  CC_REQUIRE((d.out_cs * es) % 16 == 0 && (d.out_co * es) % 16 == 0, "conv_gemm: output slice not 16-B aligned");
+  if (d.res) CC_REQUIRE((d.res_cs * es) % 16 == 0 && (d.res_co * es) % 16 == 0, "conv_gemm: residual slice not 16-B aligned");
+
+  GemmParams& p = L->p;
+  memset(&p, 0, sizeof(p));
+  const int Hout = d.stride == 2 ? d.Hin / 2 : d.Hin;
+  const int Wout = d.stride == 2 ? d.Win / 2 : d.Win;
+  p.W = Wout; p.H = Hout; p.N = d.N;
+
+  // ---- K blocking
+  p.BK = (d.Cin % 64 == 0) ? 64 : (d.Cin % 32 == 0 ? 32 : 16);
+  p.num_taps = d.k * d.k;
+  p.chunks_per_tap = d.Cin / p.BK;
+  // ---- N blocking
+  int BN = d.bn_override;
+  if (BN == 0) {
+    const int maxbn = d.out_f32 ? 128 : 256;
+    if (d.Cout <= maxbn) BN = d.Cout;
+    else {
+      for (int c : {256, 128, 64, 32, 16})
+        if (c <= maxbn && d.Cout % c == 0) { BN = c; break; }
+    }
+    // prefer 128 when it gives more tiles than SMs only with the smaller block (fill the machine)
+    if (BN == 256) {
+      const long long mt = (static_cast<long long>(d.N) * Hout * Wout + 127) / 128;
+      if (mt * (d.Cout / 256) < num_sms) BN = 128;
+    }
+  }
+  CC_REQUIRE(BN % 16 == 0 && BN >= 16 && BN <= 256 && d.Cout % BN == 0, "conv_gemm: bad BN=%d for Cout=%d", BN, d.Cout);
+  p.BN = BN;
+  p.n_blocks = d.Cout / BN;
+  p.cout = d.Cout;
+
+  // ---- M tile box: maximise useful pixels per 128-row tile
+  int best[3] = {7, 0, 0};
+  double best_eff = -1;
+  for (int lw = 0; lw <= 7; ++lw)
+    for (int lh = 0; lw + lh <= 7; ++lh) {
+      const int ln = 7 - lw - lh;
+      const int tw = 1 << lw, th = 1 << lh, tn = 1 << ln;
+      if (tw > 256 || th > 256 || tn > 256) continue;
+      const double cover = double((Wout + tw - 1) / tw * tw) * ((Hout + th - 1) / th * th) * ((d.N + tn - 1) / tn * tn);
+      double eff = double(Wout) * Hout * d.N / cover + 1e-6 * lw - 1e-7 * ln;  // ties: wider rows, fewer images
+      if (eff > best_eff) { best_eff = eff; best[0] = lw; best[1] = lh; best[2] = ln; }
+    }
+  p.lTW = best[0]; p.lTH = best[1]; p.lTN = best[2];
+  const int TW = 1 << p.lTW, TH = 1 << p.lTH, TN = 1 << p.lTN;
+  p.tiles_w = (Wout + TW - 1) / TW;
+  p.tiles_h = (Hout + TH - 1) / TH;
+  p.tiles_n = (d.N + TN - 1) / TN;
+  p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_blocks;
+  p.s2 = d.stride == 2;
+  p.ab_fmt = 1;
+
+  // ---- taps
+  const int pad = d.k / 2;
+  for (int r = 0; r < d.k; ++r)
+    for (int s = 0; s < d.k; ++s) {
+      int* t = p.tap[r * d.k + s];
+      if (!p.s2) {
+        t[0] = 0; t[1] = s - pad; t[2] = r - pad; t[3] = 0;
+      } else {
+        // input col 2x+s-1: s=0 -> (pair x-1, odd), s=1 -> (pair x, even), s=2 -> (pair x, odd); same for rows
+        const int wp = (s == 1) ? 0 : 1, dw = (s == 0) ? -1 : 0;
+        const int hp = (r == 1) ? 0 : 1, dh = (r == 0) ? -1 : 0;
+        t[0] = wp * d.in_cs; t[1] = dw; t[2] = hp; t[3] = dh;
+      }
+    }
+
+  // ---- tensor maps
+  const CUtensorMapSwizzle swz = p.BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                               : p.BK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  {
+    void* base = const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(d.in)) + size_t(d.in_co) * 2;
+    CC_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "conv_gemm: input slice not 16-B aligned");
+    cuuint64_t dims[5], strides[4];
+    cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
+    const cuuint64_t px = cuuint64_t(d.in_cs) * 2;  // bytes per pixel
+    if (!p.s2) {
+      dims[0] = d.Cin; dims[1] = d.Win; dims[2] = d.Hin; dims[3] = d.N; dims[4] = 1;
+      strides[0] = px; strides[1] = px * d.Win; strides[2] = px * d.Win * d.Hin; strides[3] = px * d.Win * d.Hin * d.N;
+      box[0] = p.BK; box[1] = TW; box[2] = TH; box[3] = TN; box[4] = 1;
+    } else {
+      dims[0] = d.in_cs + d.Cin; dims[1] = d.Win / 2; dims[2] = 2; dims[3] = d.Hin / 2; dims[4] = d.N;
+      strides[0] = 2 * px; strides[1] = px * d.Win; strides[2] = 2 * px * d.Win; strides[3] = px * d.Win * d.Hin;
+      box[0] = p.BK; box[1] = TW; box[2] = 1; box[3] = TH; box[4] = TN;
+    }
+    CUresult r = enc(&p.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CC_REQUIRE(r == CUDA_SUCCESS, "conv_gemm: cuTensorMapEncodeTiled(A) failed: %d (dims %llu,%llu,%llu,%llu,%llu)", int(r),
+               dims[0], dims[1], dims[2], dims[3], dims[4]);
+  }
+  {
+    const cuuint64_t Ktot = cuuint64_t(d.k) * d.k * d.Cin;
+    cuuint64_t dims[2] = {Ktot, cuuint64_t(d.Cout)};
+    cuuint64_t strides[1] = {Ktot * 2};
+    cuuint32_t box[2] = {cuuint32_t(p.BK), cuuint32_t(BN)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d.w), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CC_REQUIRE(r == CUDA_SUCCESS, "conv_gemm: cuTensorMapEncodeTiled(B) failed: %d", int(r));
+  }
+
+  // ---- epilogue
+  p.out = d.out; p.out_cs = d.out_cs; p.out_co = d.out_co; p.out_f32 = d.out_f32;
+  p.bias = d.bias; p.act = d.act;
+  p.res = d.res; p.res_cs = d.res_cs; p.res_co = d.res_co;
+
+  // ---- smem budget -> pipeline depth
+  const int CH = d.out_f32 ? (BN < 64 ? BN : 64) : (BN < 128 ? BN : 128);
+  const int pitch = CH * es + 16;
+  const int staging = (kTileM * pitch + 15) & ~15;
+  const int stage_bytes = kTileM * p.BK * 2 + BN * p.BK * 2;
+  const int fixed = 1024 /*align slack*/ + staging + 256 /*barriers*/;
+  int S = (kMaxSmem - fixed) / stage_bytes;
+  if (S > 8) S = 8;
+  const int num_kb = p.num_taps * p.chunks_per_tap;
+  if (S > num_kb + 1 && num_kb >= 2) S = num_kb + 1;  // no point in more stages than k-blocks (+1 for the next tile)
+  CC_REQUIRE(S >= 2, "conv_gemm: tile does not fit shared memory (BN=%d BK=%d)", BN, p.BK);
+  p.stages = S;
+  L->smem_bytes = fixed + S * stage_bytes;
+  L->grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  L->flops = 2.0 * double(d.N) * Hout * Wout * d.Cout * d.k * d.k * d.Cin;
+  return CC_OK;
+}
+
+int conv_gemm_launch(const GemmLaunch& L, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CC_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    attr_set = true;
+  }
+  conv_gemm_kernel<<<L.grid, kThreads, L.smem_bytes, stream>>>(L.p);
+  CC_CHECK_CUDA(cudaGetLastError());
+  return CC_OK;
+}
+
+}  // namespace cc
