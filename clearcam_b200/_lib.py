@@ -18,11 +18,24 @@ _lib = None
 
 _vp = ctypes.c_void_p
 _i = ctypes.c_int
+_f = ctypes.c_float
 _SIGS = {
     "cc_version": (_i, []),
     "cc_last_error": (ctypes.c_char_p, []),
     "cc_device_check": (_i, []),
     "cc_conv2d": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp]),
+    "cc_yolo_create": (_i, [ctypes.c_char_p, _i, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(_vp),
+                            ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(_vp)]),
+    "cc_yolo_destroy": (_i, [_vp]),
+    "cc_yolo_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "cc_yolo_plan_info": (_i, [_vp, _i, _i, _i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i),
+                               ctypes.POINTER(_i), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
+    "cc_yolo_layer_output": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, ctypes.POINTER(_i), ctypes.POINTER(_i),
+                                  ctypes.POINTER(_i), _vp]),
+    "cc_detect_postprocess": (_i, [_vp, _i, _i, _i, _f, _i, _f, _f, _f, _f, _f, _vp, _vp]),
+    "cc_detect_decode": (_i, [ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_i), ctypes.POINTER(_i), _i, _f,
+                              _vp, _vp, _vp]),
+    "cc_letterbox": (_i, [_vp, _i, _i, _i, _i, _i, _vp, ctypes.POINTER(_i), ctypes.POINTER(_i), _vp]),
 }
 
 

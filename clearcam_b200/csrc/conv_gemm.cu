@@ -266,12 +266,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 
 // ------------------------------------------------------------------------------------------------ host
 
-static int ilog2(int x) {
-  int l = 0;
-  while ((1 << l) < x) ++l;
-  return l;
-}
-
 bool conv_gemm_supported(const ConvDesc& d) {
   if (d.Cin % 16 != 0 || d.Cout % 16 != 0) return false;
   if (!(d.k == 1 || d.k == 3)) return false;
@@ -304,16 +298,12 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
   int BN = d.bn_override;
   if (BN == 0) {
     const int maxbn = d.out_f32 ? 128 : 256;
-    if (d.Cout <= maxbn) BN = d.Cout;
-    else {
-      for (int c : {256, 128, 64, 32, 16})
-        if (c <= maxbn && d.Cout % c == 0) { BN = c; break; }
-    }
-    // prefer 128 when it gives more tiles than SMs only with the smaller block (fill the machine)
-    if (BN == 256) {
-      const long long mt = (static_cast<long long>(d.N) * Hout * Wout + 127) / 128;
-      if (mt * (d.Cout / 256) < num_sms) BN = 128;
-    }
+    // largest multiple of 16 that divides Cout and fits the tile limit
+    for (BN = (d.Cout < maxbn ? d.Cout : maxbn) & ~15; BN >= 16; BN -= 16)
+      if (d.Cout % BN == 0) break;
+    // if the machine would be under-filled, halve the N tile (more, smaller tiles)
+    const long long mt = (static_cast<long long>(d.N) * Hout * Wout + 127) / 128;
+    while (BN > 64 && (BN / 2) % 16 == 0 && mt * (d.Cout / BN) < num_sms) BN /= 2;
   }
   CC_REQUIRE(BN % 16 == 0 && BN >= 16 && BN <= 256 && d.Cout % BN == 0, "conv_gemm: bad BN=%d for Cout=%d", BN, d.Cout);
   p.BN = BN;

@@ -22,4 +22,61 @@ struct DirectConvParams {
 };
 int conv_direct_launch(const DirectConvParams& p, cudaStream_t stream);
 
+// A bf16 NHWC tensor slice.
+struct TSlice {
+  __nv_bfloat16* p; int cs, co, C;   // buffer base, channels per pixel, first channel, channel count
+  int N, H, W;
+};
+
+// avg_pool2d(k=2,s=1,p=0) written into a same-size map whose last row/col are zero (so the stride-2 conv that
+// follows can use the even "pixel pair" TMA view).  detection/yolov9.py:47 (ADown), :62 (AConv).
+int avgpool2_pad_launch(const TSlice& in, const TSlice& out, cudaStream_t s);
+// max_pool2d(k=3,s=2,p=1) of avg_pool2d(k=2,s=1) in one pass (ADown second branch, detection/yolov9.py:47-50).
+int avgmax_pool_launch(const TSlice& in, const TSlice& out, cudaStream_t s);
+// max_pool2d(k=5,s=1,p=2)  (SP, detection/yolov9.py:127-132)
+int maxpool5_launch(const TSlice& in, const TSlice& out, cudaStream_t s);
+// nearest x2 upsample (Upsample, detection/yolov9.py:285-292)
+int upsample2_launch(const TSlice& in, const TSlice& out, cudaStream_t s);
+// CBFuse (detection/yolov9.py:230-245): out = sum_i nearest_resize(src_i) + last
+struct CBFuseParams { TSlice src[5]; int nsrc; TSlice last; TSlice out; };
+int cbfuse_launch(const CBFuseParams& p, cudaStream_t s);
+
+// Letterbox: bilinear resize (utils/helpers.py:127-131 semantics, W axis first then H, result cast to the
+// input dtype after each axis) + zero pad (detection/yolov9.py:390-404).  HWC, 3 channels, u8 or f32.
+struct LetterboxParams {
+  const void* in; void* out; int is_f32;
+  int B, Hin, Win, Hr, Wr, pad_y, pad_x, Hout, Wout;   // resized extent, pads, final extent
+  float sx, sy;                                        // float(Win/Wr), float(Hin/Hr) computed in double on the host
+};
+int letterbox_launch(const LetterboxParams& p, cudaStream_t s);
+
+// Stem: frame[..., ::-1]/255 -> Conv 3x3 s2 p1 (Cin=3) -> bias -> SiLU -> NHWC bf16
+// (detection/yolov9.py:378-379 fused into model[0] / model[1],model[15] of size e).  fp32 weights [Cout][3][3][3] (RGB order).
+struct StemParams {
+  const void* in; int is_f32; int B, H, W;    // HWC BGR frame(s)
+  const float* w; const float* bias; int Cout;
+  TSlice out;                                  // [B,H/2,W/2,Cout]
+};
+int stem_launch(const StemParams& p, cudaStream_t s);
+
+// Detect head tail: DFL softmax-expectation, dist2bbox, x stride, sigmoid, max/argmax, conf threshold
+// (detection/yolov9.py:209-219, 273-282, 263-271, 440-448).  Inputs are the fp32 logits of the three scales.
+struct DecodeParams {
+  const float* box[3]; const float* cls[3];   // [B,h,w,64], [B,h,w,80] fp32
+  int h[3], w[3]; float stride[3];
+  int B, A;                                   // A = sum h*w
+  float conf_thr;
+  float* pred;                                // [B,A,6] x1,y1,x2,y2,prob(>=thr else 0),class
+  float* raw;                                 // optional [B,84,A] (xc,yc,w,h,80 probs) for parity taps, or nullptr
+};
+int decode_launch(const DecodeParams& p, cudaStream_t s);
+
+// postprocess tail (detection/yolov9.py:449-458) + scale_boxes/clip_boxes (:406-421), one CTA per image.
+struct PostParams {
+  const float* pred; int B, A; int max_det; float iou_thr;
+  float pad_x, pad_y, gain, clip_w, clip_h; int do_scale;
+  float* out;                                 // [B,max_det,6]
+};
+int postprocess_launch(const PostParams& p, cudaStream_t s);
+
 }  // namespace cc

@@ -1,0 +1,362 @@
+// Memory-bound NHWC kernels of the detector: pools, upsample, CBFuse, letterbox, stem.
+// All are HBM/L2-bound byte movers: one thread = one output pixel x 8 channels (one 16-byte vector), consecutive
+// threads = consecutive channel vectors then consecutive pixels -> fully coalesced 16-B accesses; grids are
+// sized to cover the tensor once (grid-stride, capped at a multiple of the 148 SMs).
+#include "ops.cuh"
+#include "cc_common.h"
+
+namespace cc {
+
+struct bf8 { float v[8]; };
+
+__device__ __forceinline__ bf8 ld8(const __nv_bfloat16* p) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  bf8 r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+    r.v[2 * i] = __bfloat162float(h.x);
+    r.v[2 * i + 1] = __bfloat162float(h.y);
+  }
+  return r;
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const bf8& r) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(r.v[2 * i], r.v[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ const __nv_bfloat16* at(const TSlice& t, int n, int h, int w, int c) {
+  return t.p + ((static_cast<long long>(n) * t.H + h) * t.W + w) * t.cs + t.co + c;
+}
+__device__ __forceinline__ __nv_bfloat16* at_w(const TSlice& t, int n, int h, int w, int c) {
+  return t.p + ((static_cast<long long>(n) * t.H + h) * t.W + w) * t.cs + t.co + c;
+}
+
+static int grid_for(long long total, int threads) {
+  long long b = (total + threads - 1) / threads;
+  const long long cap = 148LL * 32;
+  return static_cast<int>(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+#define CC_GRID_STRIDE(idx, total) \
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < (total); \
+       idx += static_cast<long long>(gridDim.x) * blockDim.x)
+
+// ---------------------------------------------------------------- avg 2x2 s1 -> same-size zero-edged map
+__global__ void avgpool2_pad_kernel(TSlice in, TSlice out) {
+  const int c8 = in.C / 8;
+  const long long total = static_cast<long long>(out.N) * out.H * out.W * c8;
+  CC_GRID_STRIDE(idx, total) {
+    const int c = static_cast<int>(idx % c8) * 8;
+    long long pix = idx / c8;
+    const int w = static_cast<int>(pix % out.W);
+    const int h = static_cast<int>((pix / out.W) % out.H);
+    const int n = static_cast<int>(pix / (static_cast<long long>(out.W) * out.H));
+    bf8 r;
+    if (h < in.H - 1 && w < in.W - 1) {
+      const bf8 a = ld8(at(in, n, h, w, c)), b = ld8(at(in, n, h, w + 1, c));
+      const bf8 d = ld8(at(in, n, h + 1, w, c)), e = ld8(at(in, n, h + 1, w + 1, c));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r.v[i] = (a.v[i] + b.v[i] + d.v[i] + e.v[i]) * 0.25f;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r.v[i] = 0.f;
+    }
+    st8(at_w(out, n, h, w, c), r);
+  }
+}
+int avgpool2_pad_launch(const TSlice& in, const TSlice& out, cudaStream_t s) {
+  CC_REQUIRE(in.C % 8 == 0 && in.co % 8 == 0 && in.cs % 8 == 0 && out.co % 8 == 0 && out.cs % 8 == 0 && in.C == out.C &&
+                 in.H == out.H && in.W == out.W, "avgpool2_pad: bad slices");
+  const long long total = static_cast<long long>(out.N) * out.H * out.W * (in.C / 8);
+  avgpool2_pad_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, out);
+  CC_CHECK_CUDA(cudaGetLastError());
+  return CC_OK;
+}
+
+// ---------------------------------------------------------------- max3x3 s2 p1 of avg2x2 s1 (ADown branch 2)
+__global__ void avgmax_pool_kernel(TSlice in, TSlice out) {
+  const int c8 = in.C / 8;
+  const int Ha = in.H - 1, Wa = in.W - 1;  // extent of the (virtual) avg-pooled map
+  const long long total = static_cast<long long>(out.N) * out.H * out.W * c8;
+  CC_GRID_STRIDE(idx, total) {
+    const int c = static_cast<int>(idx % c8) * 8;
+    long long pix = idx / c8;
+    const int ox = static_cast<int>(pix % out.W);
+    const int oy = static_cast<int>((pix / out.W) % out.H);
+    const int n = static_cast<int>(pix / (static_cast<long long>(out.W) * out.H));
+    bf8 m;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m.v[i] = -INFINITY;
+    // avg rows 2oy-1..2oy+1 need input rows 2oy-1..2oy+2
+    const int y0 = 2 * oy - 1, x0 = 2 * ox - 1;
+    for (int ay = 0; ay < 3; ++ay) {
+      const int y = y0 + ay;
+      if (y < 0 || y >= Ha) continue;
+      for (int ax = 0; ax < 3; ++ax) {
+        const int x = x0 + ax;
+        if (x < 0 || x >= Wa) continue;
+        const bf8 a = ld8(at(in, n, y, x, c)), b = ld8(at(in, n, y, x + 1, c));
+        const bf8 d = ld8(at(in, n, y + 1, x, c)), e = ld8(at(in, n, y + 1, x + 1, c));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          // round the average to bf16 first: the reference max-pools the stored avg map
+          const float av = __bfloat162float(__float2bfloat16_rn((a.v[i] + b.v[i] + d.v[i] + e.v[i]) * 0.25f));
+          m.v[i] = fmaxf(m.v[i], av);
+        }
+      }
+    }
+    st8(at_w(out, n, oy, ox, c), m);
+  }
+}
+int avgmax_pool_launch(const TSlice& in, const TSlice& out, cudaStream_t s) {
+  CC_REQUIRE(in.C % 8 == 0 && in.co % 8 == 0 && in.cs % 8 == 0 && out.co % 8 == 0 && out.cs % 8 == 0 && in.C == out.C,
+             "avgmax_pool: bad slices");
+  CC_REQUIRE(out.H == (in.H - 1 + 2 - 3) / 2 + 1 && out.W == (in.W - 1 + 2 - 3) / 2 + 1, "avgmax_pool: bad output extent");
+  const long long total = static_cast<long long>(out.N) * out.H * out.W * (in.C / 8);
+  avgmax_pool_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, out);
+  CC_CHECK_CUDA(cudaGetLastError());
+  return CC_OK;
+}
+
+// ---------------------------------------------------------------- max 5x5 s1 p2
+__global__ void maxpool5_kernel(TSlice in, TSlice out) {
+  const int c8 = in.C / 8;
+  const long long total = static_cast<long long>(out.N) * out.H * out.W * c8;
+  CC_GRID_STRIDE(idx, total) {
+    const int c = static_cast<int>(idx % c8) * 8;
+    long long pix = idx / c8;
+    const int w = static_cast<int>(pix % out.W);
+    const int h = static_cast<int>((pix / out.W) % out.H);
+    const int n = static_cast<int>(pix / (static_cast<long long>(out.W) * out.H));
+    bf8 m;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m.v[i] = -INFINITY;
+    for (int dy = -2; dy <= 2; ++dy) {
+      const int y = h + dy;
+      if (y < 0 || y >= in.H) continue;
+      for (int dx = -2; dx <= 2; ++dx) {
+        const int x = w + dx;
+        if (x < 0 || x >= in.W) continue;
+        const bf8 a = ld8(at(in, n, y, x, c));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m.v[i] = fmaxf(m.v[i], a.v[i]);
+      }
+    }
+    st8(at_w(out, n, h, w, c), m);
+  }
+}
+int maxpool5_launch(const TSlice& in, const TSlice& out, cudaStream_t s) {
+  CC_REQUIRE(in.C % 8 == 0 && in.co % 8 == 0 && in.cs % 8 == 0 && out.co % 8 == 0 && out.cs % 8 == 0 && in.C == out.C &&
+                 in.H == out.H && in.W == out.W, "maxpool5: bad slices");
+  const long long total = static_cast<long long>(out.N) * out.H * out.W * (in.C / 8);
+  maxpool5_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, out);
+  CC_CHECK_CUDA(cudaGetLastError());
+  return CC_OK;
+}
+
+// ---------------------------------------------------------------- nearest x2
+__global__ void upsample2_kernel(TSlice in, TSlice out) {
+  const int c8 = in.C / 8;
+  const long long total = static_cast<long long>(out.N) * out.H * out.W * c8;
+  CC_GRID_STRIDE(idx, total) {
+    const int c = static_cast<int>(idx % c8) * 8;
+    long long pix = idx / c8;
+    const int w = static_cast<int>(pix % out.W);
+    const int h = static_cast<int>((pix / out.W) % out.H);
+    const int n = static_cast<int>(pix / (static_cast<long long>(out.W) * out.H));
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(at(in, n, h >> 1, w >> 1, c)));
+    *reinterpret_cast<uint4*>(at_w(out, n, h, w, c)) = v;
+  }
+}
+int upsample2_launch(const TSlice& in, const TSlice& out, cudaStream_t s) {
+  CC_REQUIRE(in.C % 8 == 0 && in.co % 8 == 0 && in.cs % 8 == 0 && out.co % 8 == 0 && out.cs % 8 == 0 && in.C == out.C &&
+                 out.H == 2 * in.H && out.W == 2 * in.W, "upsample2: bad slices");
+  const long long total = static_cast<long long>(out.N) * out.H * out.W * (in.C / 8);
+  upsample2_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, out);
+  CC_CHECK_CUDA(cudaGetLastError());
+  return CC_OK;
+}
+
+// ---------------------------------------------------------------- CBFuse
+__global__ void cbfuse_kernel(CBFuseParams p) {
+  const int c8 = p.out.C / 8;
+  const long long total = static_cast<long long>(p.out.N) * p.out.H * p.out.W * c8;
+  CC_GRID_STRIDE(idx, total) {
+    const int c = static_cast<int>(idx % c8) * 8;
+    long long pix = idx / c8;
+    const int w = static_cast<int>(pix % p.out.W);
+    const int h = static_cast<int>((pix / p.out.W) % p.out.H);
+    const int n = static_cast<int>(pix / (static_cast<long long>(p.out.W) * p.out.H));
+    bf8 acc;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc.v[i] = 0.f;
+    for (int k = 0; k < p.nsrc; ++k) {
+      // nearest: src = floor(dst * in / out)
+      const int sh = static_cast<int>((static_cast<long long>(h) * p.src[k].H) / p.out.H);
+      const int sw = static_cast<int>((static_cast<long long>(w) * p.src[k].W) / p.out.W);
+      const bf8 a = ld8(at(p.src[k], n, sh, sw, c));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc.v[i] = (k == 0) ? a.v[i] : acc.v[i] + a.v[i];
+    }
+    const bf8 l = ld8(at(p.last, n, h, w, c));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc.v[i] += l.v[i];
+    st8(at_w(p.out, n, h, w, c), acc);
+  }
+}
+int cbfuse_launch(const CBFuseParams& p, cudaStream_t s) {
+  CC_REQUIRE(p.nsrc >= 1 && p.nsrc <= 5 && p.out.C % 8 == 0, "cbfuse: bad params");
+  const long long total = static_cast<long long>(p.out.N) * p.out.H * p.out.W * (p.out.C / 8);
+  cbfuse_kernel<<<grid_for(total, 256), 256, 0, s>>>(p);
+  CC_CHECK_CUDA(cudaGetLastError());
+  return CC_OK;
+}
+
+// ---------------------------------------------------------------- letterbox (bilinear, reference semantics)
+__device__ __forceinline__ void lerp_idx(int i, int n_in, float scale, int& lo, int& hi, float& w) {
+  // idx = clip((i+0.5)*in/out - 0.5, 0, in-1); `scale` = float(in/out) computed on the host in double
+  float idx = __fsub_rn(__fmul_rn(static_cast<float>(i) + 0.5f, scale), 0.5f);
+  idx = fminf(fmaxf(idx, 0.f), static_cast<float>(n_in - 1));
+  lo = static_cast<int>(floorf(idx));
+  hi = static_cast<int>(ceilf(idx));
+  w = idx - static_cast<float>(lo);
+}
+__device__ __forceinline__ int lerp_u8(int a, int b, int wi) {
+  int diff = ((b - a + 128) & 255) - 128;     // int8 wrap-around of the reference's uint8 subtraction
+  return (a + ((diff * wi + 64) >> 7)) & 255;
+}
+__global__ void letterbox_kernel(LetterboxParams p) {
+  const long long total = static_cast<long long>(p.B) * p.Hout * p.Wout;
+  CC_GRID_STRIDE(idx, total) {
+    const int x = static_cast<int>(idx % p.Wout);
+    const int y = static_cast<int>((idx / p.Wout) % p.Hout);
+    const int n = static_cast<int>(idx / (static_cast<long long>(p.Wout) * p.Hout));
+    const int ry = y - p.pad_y, rx = x - p.pad_x;
+    const bool inside = ry >= 0 && ry < p.Hr && rx >= 0 && rx < p.Wr;
+    int xl = 0, xh = 0, yl = 0, yh = 0;
+    float wx = 0.f, wy = 0.f;
+    if (inside) {
+      if (p.Wr != p.Win) lerp_idx(rx, p.Win, p.sx, xl, xh, wx); else { xl = xh = rx; }
+      if (p.Hr != p.Hin) lerp_idx(ry, p.Hin, p.sy, yl, yh, wy); else { yl = yh = ry; }
+    }
+    if (p.is_f32) {
+      const float* src = static_cast<const float*>(p.in) + static_cast<long long>(n) * p.Hin * p.Win * 3;
+      float* dst = static_cast<float*>(p.out) + idx * 3;
+      for (int c = 0; c < 3; ++c) {
+        float r = 0.f;
+        if (inside) {
+          const float a = src[(static_cast<long long>(yl) * p.Win + xl) * 3 + c], b = src[(static_cast<long long>(yl) * p.Win + xh) * 3 + c];
+          const float d = src[(static_cast<long long>(yh) * p.Win + xl) * 3 + c], e = src[(static_cast<long long>(yh) * p.Win + xh) * 3 + c];
+          const float top = __fadd_rn(a, __fmul_rn(__fsub_rn(b, a), wx));
+          const float bot = __fadd_rn(d, __fmul_rn(__fsub_rn(e, d), wx));
+          r = __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), wy));
+        }
+        dst[c] = r;
+      }
+    } else {
+      const uint8_t* src = static_cast<const uint8_t*>(p.in) + static_cast<long long>(n) * p.Hin * p.Win * 3;
+      uint8_t* dst = static_cast<uint8_t*>(p.out) + idx * 3;
+      const int wxi = static_cast<int>(static_cast<short>(wx * 128.f + 0.5f));
+      const int wyi = static_cast<int>(static_cast<short>(wy * 128.f + 0.5f));
+      for (int c = 0; c < 3; ++c) {
+        int r = 0;
+        if (inside) {
+          const int a = src[(static_cast<long long>(yl) * p.Win + xl) * 3 + c], b = src[(static_cast<long long>(yl) * p.Win + xh) * 3 + c];
+          const int d = src[(static_cast<long long>(yh) * p.Win + xl) * 3 + c], e = src[(static_cast<long long>(yh) * p.Win + xh) * 3 + c];
+          const int top = (p.Wr != p.Win) ? lerp_u8(a, b, wxi) : a;
+          const int bot = (p.Wr != p.Win) ? lerp_u8(d, e, wxi) : d;
+          r = (p.Hr != p.Hin) ? lerp_u8(top, bot, wyi) : top;
+        }
+        dst[c] = static_cast<uint8_t>(r);
+      }
+    }
+  }
+}
+int letterbox_launch(const LetterboxParams& p, cudaStream_t s) {
+  const long long total = static_cast<long long>(p.B) * p.Hout * p.Wout;
+  letterbox_kernel<<<grid_for(total, 256), 256, 0, s>>>(p);
+  CC_CHECK_CUDA(cudaGetLastError());
+  return CC_OK;
+}
+
+// ---------------------------------------------------------------- stem conv (Cin = 3)
+// block = 128 threads = 128 consecutive output pixels of one row-major run; weights (27 x Cout fp32) in smem.
+// Each thread gathers its 27 inputs once (RGB order, /255) and produces all Cout channels, 16 at a time.
+template <bool F32>
+__global__ void __launch_bounds__(128) stem_kernel(StemParams p) {
+  extern __shared__ float sw[];  // [27][Cout] then bias[Cout]
+  const int Cout = p.Cout;
+  for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) {
+    const int co = i % Cout, k = i / Cout;  // k = (r*3+s)*3 + c
+    sw[i] = p.w[co * 27 + k];
+  }
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[27 * Cout + i] = p.bias[i];
+  __syncthreads();
+  const int Ho = p.H / 2, Wo = p.W / 2;
+  const long long total = static_cast<long long>(p.B) * Ho * Wo;
+  CC_GRID_STRIDE(idx, total) {
+    const int ox = static_cast<int>(idx % Wo);
+    const int oy = static_cast<int>((idx / Wo) % Ho);
+    const int n = static_cast<int>(idx / (static_cast<long long>(Wo) * Ho));
+    float in[27];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int iy = 2 * oy + r - 1;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int ix = 2 * ox + s - 1;
+        const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+        const long long off = ((static_cast<long long>(n) * p.H + iy) * p.W + ix) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float v = 0.f;
+          if (ok) {
+            // channel flip: network channel c (RGB) = frame channel 2-c (BGR);  x/255 as an IEEE division
+            if (F32) v = static_cast<const float*>(p.in)[off + 2 - c];
+            else v = static_cast<float>(static_cast<const uint8_t*>(p.in)[off + 2 - c]);
+            v = __fdiv_rn(v, 255.0f);
+          }
+          in[(r * 3 + s) * 3 + c] = v;
+        }
+      }
+    }
+    __nv_bfloat16* dst = p.out.p + ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * p.out.cs + p.out.co;
+    for (int c0 = 0; c0 < Cout; c0 += 8) {
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = sw[27 * Cout + c0 + j];
+#pragma unroll
+      for (int k = 0; k < 27; ++k) {
+        const float4 w0 = *reinterpret_cast<const float4*>(&sw[k * Cout + c0]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&sw[k * Cout + c0 + 4]);
+        acc[0] = fmaf(in[k], w0.x, acc[0]); acc[1] = fmaf(in[k], w0.y, acc[1]);
+        acc[2] = fmaf(in[k], w0.z, acc[2]); acc[3] = fmaf(in[k], w0.w, acc[3]);
+        acc[4] = fmaf(in[k], w1.x, acc[4]); acc[5] = fmaf(in[k], w1.y, acc[5]);
+        acc[6] = fmaf(in[k], w1.z, acc[6]); acc[7] = fmaf(in[k], w1.w, acc[7]);
+      }
+      bf8 o;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o.v[j] = __fdividef(acc[j], 1.0f + __expf(-acc[j]));
+      st8(dst + c0, o);
+    }
+  }
+}
+int stem_launch(const StemParams& p, cudaStream_t s) {
+  CC_REQUIRE(p.Cout % 8 == 0 && p.H % 2 == 0 && p.W % 2 == 0 && p.out.cs % 8 == 0 && p.out.co % 8 == 0, "stem: bad shape");
+  const long long total = static_cast<long long>(p.B) * (p.H / 2) * (p.W / 2);
+  const int smem = (27 + 1) * p.Cout * sizeof(float);
+  long long blocks = (total + 127) / 128;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  if (p.is_f32) stem_kernel<true><<<static_cast<int>(blocks), 128, smem, s>>>(p);
+  else stem_kernel<false><<<static_cast<int>(blocks), 128, smem, s>>>(p);
+  CC_CHECK_CUDA(cudaGetLastError());
+  return CC_OK;
+}
+
+}  // namespace cc

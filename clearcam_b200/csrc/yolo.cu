@@ -1,0 +1,797 @@
+// YOLOv9 (t/s/c/e) forward as a static op list over the sm_100a kernels.
+//
+// What it replaces in the reference: YOLOv9.__init__ graph (detection/yolov9.py:299-371), YOLOv9.__call__
+// (:375-388: preprocess -> BGR flip -> /255 -> layer routing by m.f -> postprocess -> scale_boxes) and the
+// TinyJit capture of jit_infer (utils/helpers.py:214-221: here a cached "plan" per input shape).
+//
+// Design (B200-first, not a translation):
+//  * a plan = flat vector of kernel launches with every tensor map / pointer resolved at build time;
+//  * Tensor.cat / chunk / split never move data: producers write straight into channel slices of the
+//    consumer's concat buffer (NHWC, channel stride = buffer width);
+//  * RepNCSP.cv1 and .cv2 (two 1x1 convs on the same input) run as ONE GEMM with concatenated output channels,
+//    likewise the first 3x3 of the box and class branches of each detect scale;
+//  * grouped (g=4) head convs become block-diagonal dense weights so they ride the tensor-core kernel too;
+//  * RepNBottleneck's residual is fused in the conv epilogue (in place);
+//  * head logits stay fp32; everything else is bf16 storage with fp32 accumulation.
+#include "clearcam_b200.h"
+#include "cc_common.h"
+#include "conv_gemm.cuh"
+#include "ops.cuh"
+#include <cmath>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace cc {
+
+// ------------------------------------------------------------------------------------------------ spec
+// Own restatement of the reference layer tables (detection/yolov9.py:299-371, SIZES :461-464).
+enum LOp { L_CONV, L_ELAN1, L_ELAN4, L_ADOWN, L_ACONV, L_SPPELAN, L_UPSAMPLE, L_CONCAT, L_SILENCE, L_CBLINEAR, L_CBFUSE, L_DETECT };
+struct Layer {
+  LOp op;
+  std::vector<int> f;          // sources (-1 = previous)
+  int a = 0, b = 0, c = 0, n = 0, k = 0, s = 0;   // op-specific ints
+  std::vector<int> list;       // c2s (cblinear) / idx (cbfuse) / chs (detect)
+};
+
+static Layer mk(LOp op, std::vector<int> f = {-1}) { Layer l; l.op = op; l.f = std::move(f); return l; }
+static Layer conv_l(int cin, int cout, int k, int s, std::vector<int> f = {-1}) {
+  Layer l = mk(L_CONV, std::move(f)); l.a = cin; l.b = cout; l.k = k; l.s = s; return l;
+}
+static Layer elan4_l(int a, int b, int c, int n) { Layer l = mk(L_ELAN4); l.a = a; l.b = b; l.c = c; l.n = n; return l; }
+static Layer adown_l(int ch) { Layer l = mk(L_ADOWN); l.a = ch; return l; }
+static Layer aconv_l(int cin, int cout) { Layer l = mk(L_ACONV); l.a = cin; l.b = cout; return l; }
+static Layer cbl_l(int cin, std::vector<int> c2s, int f) { Layer l = mk(L_CBLINEAR, {f}); l.a = cin; l.list = std::move(c2s); return l; }
+static Layer cbf_l(std::vector<int> f, std::vector<int> idx) { Layer l = mk(L_CBFUSE, std::move(f)); l.list = std::move(idx); return l; }
+
+static bool build_spec(const std::string& size, std::vector<Layer>* out) {
+  std::vector<Layer>& L = *out;
+  static const std::map<std::string, std::vector<int>> SZ = {
+      {"t", {16, 64, 96, 24, 128, 256, 224, 160, 48, 144, 192, 80, 32, 16, 3, 96, 32, 64, 128, 64, 64, 128}},
+      {"s", {32, 128, 192, 48, 256, 512, 448, 320, 96, 288, 384, 128, 64, 32, 3, 192, 64, 64, 128, 128, 128, 256}},
+      {"m", {32, 240, 360, 90, 480, 960, 840, 600, 184, 544, 720, 240, 128, 60, 1, 360, 120, 64, 128, 240, 240, 480}},
+      {"c", {64, 256, 512, 128, 256, 1024, 1024, 1024, 128, 768, 1024, 256, 128, 64, 1, 256, 128, 128, 256, 128, 512, 512}}};
+  if (size == "e") {
+    L.push_back(mk(L_SILENCE));
+    L.push_back(conv_l(3, 64, 3, 2));
+    L.push_back(conv_l(64, 128, 3, 2));
+    L.push_back(elan4_l(128, 32, 256, 2));
+    L.push_back(adown_l(128));
+    L.push_back(elan4_l(256, 64, 512, 2));
+    L.push_back(adown_l(256));
+    L.push_back(elan4_l(512, 128, 1024, 2));
+    L.push_back(adown_l(512));
+    L.push_back(elan4_l(1024, 128, 1024, 2));
+    L.push_back(cbl_l(64, {64}, 1));
+    L.push_back(cbl_l(256, {64, 128}, 3));
+    L.push_back(cbl_l(512, {64, 128, 256}, 5));
+    L.push_back(cbl_l(1024, {64, 128, 256, 512}, 7));
+    L.push_back(cbl_l(1024, {64, 128, 256, 512, 1024}, 9));
+    L.push_back(conv_l(3, 64, 3, 2, {0}));
+    L.push_back(cbf_l({10, 11, 12, 13, 14, -1}, {0, 0, 0, 0, 0}));
+    L.push_back(conv_l(64, 128, 3, 2));
+    L.push_back(cbf_l({11, 12, 13, 14, -1}, {1, 1, 1, 1}));
+    L.push_back(elan4_l(128, 32, 256, 2));
+    L.push_back(adown_l(128));
+    L.push_back(cbf_l({12, 13, 14, -1}, {2, 2, 2}));
+    L.push_back(elan4_l(256, 64, 512, 2));
+    L.push_back(adown_l(256));
+    L.push_back(cbf_l({13, 14, -1}, {3, 3}));
+    L.push_back(elan4_l(512, 128, 1024, 2));
+    L.push_back(adown_l(512));
+    L.push_back(cbf_l({14, -1}, {4}));
+    L.push_back(elan4_l(1024, 128, 1024, 2));
+    { Layer l = mk(L_SPPELAN, {28}); l.a = 1024; l.b = 256; l.c = 512; L.push_back(l); }
+    L.push_back(mk(L_UPSAMPLE));
+    L.push_back(mk(L_CONCAT, {-1, 25}));
+    L.push_back(elan4_l(1536, 128, 512, 2));
+    L.push_back(mk(L_UPSAMPLE));
+    L.push_back(mk(L_CONCAT, {-1, 22}));
+    L.push_back(elan4_l(1024, 64, 256, 2));
+    L.push_back(adown_l(128));
+    L.push_back(mk(L_CONCAT, {-1, 32}));
+    L.push_back(elan4_l(768, 128, 512, 2));
+    L.push_back(adown_l(256));
+    L.push_back(mk(L_CONCAT, {-1, 29}));
+    L.push_back(elan4_l(1024, 256, 512, 2));
+    { Layer l = mk(L_DETECT, {35, 38, 41}); l.list = {256, 512, 512}; l.a = 256; L.push_back(l); }
+    return true;
+  }
+  auto it = SZ.find(size);
+  if (it == SZ.end()) return false;
+  const std::vector<int>& z = it->second;
+  const int a = z[0], b = z[1], c = z[2], d = z[3], e = z[4], f = z[5], g = z[6], h = z[7], i = z[8], j = z[9], k = z[10],
+            l = z[11], m = z[12], n = z[13], p = z[14], q = z[15], r = z[16], s = z[17], t = z[18], u = z[19], v = z[20],
+            w = z[21];
+  const bool small = size == "t" || size == "s";
+  const bool isc = size == "c";
+  L.push_back(conv_l(3, a, 3, 2));
+  L.push_back(conv_l(a, a * 2, 3, 2));
+  if (small) { Layer x = mk(L_ELAN1); x.a = a * 2; x.b = m; x.c = a; x.n = b; L.push_back(x); }
+  else L.push_back(elan4_l(s, 32, t, p));
+  L.push_back(isc ? adown_l(128) : aconv_l(m, u));
+  L.push_back(elan4_l(b, n, v, p));
+  L.push_back(isc ? adown_l(256) : aconv_l(b, q));
+  L.push_back(elan4_l(c, d, c, p));
+  L.push_back(isc ? adown_l(256) : aconv_l(q, e));
+  L.push_back(elan4_l(w, r, w, p));
+  { Layer x = mk(L_SPPELAN); x.a = w; x.b = b; x.c = w; (void)f; L.push_back(x); }
+  L.push_back(mk(L_UPSAMPLE));
+  L.push_back(mk(L_CONCAT, {-1, 6}));
+  L.push_back(elan4_l(g, d, c, p));
+  L.push_back(mk(L_UPSAMPLE));
+  L.push_back(mk(L_CONCAT, {-1, 4}));
+  L.push_back(elan4_l(h, n, b, p));
+  L.push_back(isc ? adown_l(128) : aconv_l(v, i));
+  L.push_back(mk(L_CONCAT, {-1, 12}));
+  L.push_back(elan4_l(j, d, c, p));
+  L.push_back(isc ? adown_l(256) : aconv_l(q, b));
+  L.push_back(mk(L_CONCAT, {-1, 9}));
+  L.push_back(elan4_l(k, r, w, p));
+  { Layer x = mk(L_DETECT, {15, 18, 21}); x.list = {b, c, w}; x.a = l; L.push_back(x); }
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------ weights
+struct HostT { const float* p; long long n; };
+struct ConvW {           // device-resident, kernel layout
+  __nv_bfloat16* w = nullptr;   // [Cout][k][k][Cin_eff]  (Cin_eff = Cin when dense, Cin/groups when grouped)
+  float* wf32 = nullptr;        // stem only: fp32 [Cout][3][3][3]
+  float* bias = nullptr;
+  int cin = 0, cout = 0, k = 0, groups = 1;   // groups == 1 -> dense (possibly block-diagonal expansion)
+};
+
+static __nv_bfloat16 f2bf(float x) { return __float2bfloat16_rn(x); }
+
+struct T { __nv_bfloat16* p = nullptr; int cs = 0, co = 0, C = 0, H = 0, W = 0; bool image = false; };
+
+struct Op {
+  enum Kind { GEMM, DIRECT, AVGPAD, AVGMAX, MAXPOOL5, UPSAMPLE, CBFUSE, LETTERBOX, STEM, DECODE, POST } kind;
+  GemmLaunch gemm;
+  DirectConvParams direct;
+  TSlice s_in, s_out;
+  CBFuseParams cbf;
+  LetterboxParams lb;
+  StemParams stem;
+  DecodeParams dec;
+  PostParams post;
+  std::string name;
+};
+
+struct YoloPlan {
+  int B = 0, Hf = 0, Wf = 0, res = 0, is_f32 = 0, H = 0, W = 0, A = 0;
+  std::vector<Op> ops;
+  std::vector<void*> allocs;
+  size_t alloc_bytes = 0;
+  float* pred = nullptr;   // [B,A,6]
+  float* raw = nullptr;    // [B,84,A] (allocated lazily when a tap is requested)
+  void* lb_out = nullptr;  // letterboxed frames (same dtype as input) or nullptr when identity
+  double conv_flops = 0;
+  int n_launch = 0;
+  std::vector<T> layer_outs;   // per spec layer (parity taps)
+  ~YoloPlan() { for (void* p : allocs) cudaFree(p); }
+};
+
+struct YoloModel {
+  std::string size;
+  std::vector<Layer> spec;
+  std::map<std::string, HostT> host;     // borrowed pointers, valid only during create
+  std::map<std::string, ConvW> convs;
+  std::vector<void*> allocs;
+  std::map<std::string, std::unique_ptr<YoloPlan>> plans;
+  int sms = 0;
+  ~YoloModel() { plans.clear(); for (void* p : allocs) cudaFree(p); }
+
+  int upload(const void* h, size_t bytes, void** d) {
+    CC_CHECK_CUDA(cudaMalloc(d, bytes));
+    allocs.push_back(*d);
+    CC_CHECK_CUDA(cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice));
+    return CC_OK;
+  }
+
+  // Load conv `name` (PyTorch layout [Cout][Cin/g][k][k]) -> [Cout][k][k][Cin] bf16, optionally expanding groups
+  // to block-diagonal dense, optionally stacking a second conv's output channels under it (fused 1x1 pair).
+  int load_conv(const std::string& key, const std::vector<std::string>& names, int cin, const std::vector<int>& couts,
+                int k, int groups, bool dense, bool stem = false) {
+    if (convs.count(key)) return CC_OK;
+    int cout_total = 0;
+    for (int c : couts) cout_total += c;
+    const int cin_g = cin / groups;
+    const int cin_eff = dense ? cin : cin_g;
+    std::vector<__nv_bfloat16> w(static_cast<size_t>(cout_total) * k * k * cin_eff, f2bf(0.f));
+    std::vector<float> wf, bias(cout_total);
+    if (stem) wf.resize(static_cast<size_t>(cout_total) * 27);
+    int co_base = 0;
+    for (size_t t = 0; t < names.size(); ++t) {
+      auto iw = host.find(names[t] + ".weight"), ib = host.find(names[t] + ".bias");
+      CC_REQUIRE(iw != host.end() && ib != host.end(), "yolo: missing weight '%s'", names[t].c_str());
+      const int cout = couts[t];
+      CC_REQUIRE(iw->second.n == static_cast<long long>(cout) * cin_g * k * k && ib->second.n == cout,
+                 "yolo: '%s' has %lld weight / %lld bias elements, expected %lld / %d", names[t].c_str(), iw->second.n,
+                 ib->second.n, static_cast<long long>(cout) * cin_g * k * k, cout);
+      const float* src = iw->second.p;
+      const int cpg_out = cout / groups;
+      for (int co = 0; co < cout; ++co) {
+        const int g = co / cpg_out;
+        for (int ci = 0; ci < cin_g; ++ci)
+          for (int r = 0; r < k; ++r)
+            for (int s = 0; s < k; ++s) {
+              const float v = src[((static_cast<size_t>(co) * cin_g + ci) * k + r) * k + s];
+              const int ci_eff = dense ? g * cin_g + ci : ci;
+              if (stem) wf[(static_cast<size_t>(co_base + co) * 9 + r * 3 + s) * 3 + ci] = v;
+              else w[((static_cast<size_t>(co_base + co) * k + r) * k + s) * cin_eff + ci_eff] = f2bf(v);
+            }
+        bias[co_base + co] = ib->second.p[co];
+      }
+      co_base += cout;
+    }
+    ConvW cw;
+    cw.cin = cin; cw.cout = cout_total; cw.k = k; cw.groups = dense ? 1 : groups;
+    int rc;
+    if (stem) { if ((rc = upload(wf.data(), wf.size() * 4, reinterpret_cast<void**>(&cw.wf32)))) return rc; }
+    else { if ((rc = upload(w.data(), w.size() * 2, reinterpret_cast<void**>(&cw.w)))) return rc; }
+    if ((rc = upload(bias.data(), bias.size() * 4, reinterpret_cast<void**>(&cw.bias)))) return rc;
+    convs[key] = cw;
+    return CC_OK;
+  }
+};
+
+static bool tc_ok(int cin, int cout) { return cin % 16 == 0 && cout % 16 == 0; }
+
+// ------------------------------------------------------------------------------------------------ plan builder
+struct Builder {
+  YoloModel& M;
+  YoloPlan& P;
+  int rc = CC_OK;
+  std::vector<T> outs;                      // per layer output (tuple outputs: see cbl)
+  std::vector<std::vector<T>> cbl_chunks;   // per layer: CBLinear chunks
+  struct Place { int concat; int co; };
+  std::map<int, Place> place;               // layer -> slice of a concat buffer
+  std::map<int, T> concat_buf;              // concat layer -> buffer
+  std::vector<int> outC;                    // inferred channels per layer
+
+  Builder(YoloModel& m, YoloPlan& p) : M(m), P(p) {}
+
+  void* dalloc(size_t bytes) {
+    void* d = nullptr;
+    if (rc) return nullptr;
+    if (cudaMalloc(&d, bytes) != cudaSuccess) { set_error("yolo plan: cudaMalloc(%zu) failed", bytes); rc = CC_ERR_CUDA; return nullptr; }
+    P.allocs.push_back(d);
+    P.alloc_bytes += bytes;
+    return d;
+  }
+  T talloc(int C, int H, int W) {
+    T t; t.cs = C; t.co = 0; t.C = C; t.H = H; t.W = W;
+    t.p = static_cast<__nv_bfloat16*>(dalloc(static_cast<size_t>(P.B) * H * W * C * 2));
+    return t;
+  }
+  static T slice(const T& t, int co, int C) { T s = t; s.co = t.co + co; s.C = C; return s; }
+  TSlice ts(const T& t) const { TSlice s; s.p = t.p; s.cs = t.cs; s.co = t.co; s.C = t.C; s.N = P.B; s.H = t.H; s.W = t.W; return s; }
+
+  // conv: in -> out slice (out.H/W must already be the conv's output extent)
+  void conv(const std::string& key, const T& in, const T& out, int stride, int act, const T* res = nullptr,
+            float* out_f32 = nullptr) {
+    if (rc) return;
+    auto it = M.convs.find(key);
+    if (it == M.convs.end()) { set_error("yolo plan: conv '%s' not loaded", key.c_str()); rc = CC_ERR_STATE; return; }
+    const ConvW& cw = it->second;
+    if (cw.cin != in.C) { set_error("yolo plan: conv '%s' expects Cin=%d, got %d", key.c_str(), cw.cin, in.C); rc = CC_ERR_INVALID; return; }
+    Op op;
+    op.name = key;
+    if (cw.groups == 1 && tc_ok(cw.cin, cw.cout)) {
+      ConvDesc d{};
+      d.in = in.p; d.in_cs = in.cs; d.in_co = in.co; d.Cin = in.C;
+      d.N = P.B; d.Hin = in.H; d.Win = in.W; d.k = cw.k; d.stride = stride;
+      d.w = cw.w; d.bias = cw.bias;
+      if (out_f32) { d.out = out_f32; d.out_cs = cw.cout; d.out_co = 0; d.out_f32 = 1; }
+      else { d.out = out.p; d.out_cs = out.cs; d.out_co = out.co; d.out_f32 = 0; }
+      d.Cout = cw.cout; d.act = act;
+      if (res) { d.res = res->p; d.res_cs = res->cs; d.res_co = res->co; }
+      op.kind = Op::GEMM;
+      rc = conv_gemm_build(d, M.sms, &op.gemm);
+      if (rc) return;
+      P.conv_flops += op.gemm.flops;
+    } else {
+      DirectConvParams& q = op.direct;
+      q = DirectConvParams{};
+      q.in = in.p; q.in_cs = in.cs; q.in_co = in.co; q.Cin = in.C;
+      q.N = P.B; q.Hin = in.H; q.Win = in.W; q.Hbuf = in.H; q.Wbuf = in.W;
+      q.k = cw.k; q.stride = stride; q.pad = cw.k / 2; q.groups = cw.groups;
+      q.w = cw.w; q.bias = cw.bias;
+      if (out_f32) { q.out = out_f32; q.out_cs = cw.cout; q.out_co = 0; q.out_f32 = 1; }
+      else { q.out = out.p; q.out_cs = out.cs; q.out_co = out.co; q.out_f32 = 0; }
+      q.Cout = cw.cout;
+      q.Hout = stride == 2 ? in.H / 2 : in.H; q.Wout = stride == 2 ? in.W / 2 : in.W;
+      q.act = act;
+      if (res) { q.res = res->p; q.res_cs = res->cs; q.res_co = res->co; }
+      op.kind = Op::DIRECT;
+      P.conv_flops += 2.0 * P.B * q.Hout * q.Wout * cw.cout * (cw.cin / cw.groups) * cw.k * cw.k;
+    }
+    P.ops.push_back(std::move(op));
+  }
+  void simple(Op::Kind kind, const T& in, const T& out, const char* name) {
+    if (rc) return;
+    Op op; op.kind = kind; op.s_in = ts(in); op.s_out = ts(out); op.name = name;
+    P.ops.push_back(std::move(op));
+  }
+
+  // destination of layer i's output: a slice of a later concat buffer, or a fresh buffer
+  T out_for(int i, int C, int H, int W) {
+    auto it = place.find(i);
+    if (it == place.end()) return talloc(C, H, W);
+    const int ci = it->second.concat;
+    if (!concat_buf.count(ci)) concat_buf[ci] = talloc(outC[ci], H, W);
+    return slice(concat_buf[ci], it->second.co, C);
+  }
+
+  // RepNCSP (detection/yolov9.py:92-105) on `x` (2b channels) -> fresh 2b-channel tensor
+  T repncsp(const std::string& pfx, const T& x, int b, int n) {
+    T t1 = talloc(2 * b, x.H, x.W);                         // [x1 | x3]
+    conv(pfx + ".cv1+cv2", x, t1, 1, CC_ACT_SILU);
+    T x1 = slice(t1, 0, b);
+    for (int i = 0; i < n; ++i) {
+      T t2 = talloc(b, x.H, x.W);
+      conv(pfx + ".m." + std::to_string(i) + ".cv1", x1, t2, 1, CC_ACT_SILU);
+      conv(pfx + ".m." + std::to_string(i) + ".cv2", t2, x1, 1, CC_ACT_SILU, &x1);   // x + cv2(cv1(x)), in place
+    }
+    T o = talloc(2 * b, x.H, x.W);
+    conv(pfx + ".cv3", t1, o, 1, CC_ACT_SILU);
+    return o;
+  }
+
+  int build();
+};
+
+static int layer_out_channels(const Layer& l, const std::vector<int>& outC, int idx) {
+  auto src = [&](int f) { return f == -1 ? outC[idx - 1] : outC[f]; };
+  switch (l.op) {
+    case L_CONV: return l.b;
+    case L_ELAN1: return l.b;
+    case L_ELAN4: return l.c;
+    case L_ADOWN: return 2 * l.a;
+    case L_ACONV: return l.b;
+    case L_SPPELAN: return l.c;
+    case L_UPSAMPLE: return src(l.f[0]);
+    case L_CONCAT: return src(l.f[0]) + src(l.f[1]);
+    case L_SILENCE: return 3;
+    case L_CBLINEAR: { int s = 0; for (int c : l.list) s += c; return s; }
+    case L_CBFUSE: return src(l.f.back());
+    case L_DETECT: return 0;
+  }
+  return 0;
+}
+
+int Builder::build() {
+  const std::vector<Layer>& S = M.spec;
+  const int nl = static_cast<int>(S.size());
+  outC.assign(nl, 0);
+  for (int i = 0; i < nl; ++i) outC[i] = layer_out_channels(S[i], outC, i);
+  // concat placement: each source of a Concat writes directly into the concat buffer
+  for (int i = 0; i < nl; ++i)
+    if (S[i].op == L_CONCAT) {
+      const int a = S[i].f[0] == -1 ? i - 1 : S[i].f[0], b = S[i].f[1] == -1 ? i - 1 : S[i].f[1];
+      if (!place.count(a) && !place.count(b) && S[a].op != L_SILENCE && S[b].op != L_SILENCE) {
+        place[a] = {i, 0};
+        place[b] = {i, outC[a]};
+      }
+    }
+
+  // ---- preprocess (detection/yolov9.py:390-404)
+  const double r = std::min(double(P.res) / P.Hf, double(P.res) / P.Wf);
+  const int new_w = int(std::nearbyint(P.Wf * r)), new_h = int(std::nearbyint(P.Hf * r));
+  double dw = double((P.res - new_w) % 32), dh = double((P.res - new_h) % 32);
+  if (dw < 0) dw += 32;
+  if (dh < 0) dh += 32;
+  dw /= 2; dh /= 2;
+  const int px = int(std::nearbyint(dw - 0.1)), py = int(std::nearbyint(dh - 0.1));
+  P.H = new_h + 2 * py; P.W = new_w + 2 * px;
+  CC_REQUIRE(P.H % 32 == 0 && P.W % 32 == 0 && P.H > 0 && P.W > 0,
+             "yolo: letterboxed input %dx%d is not a multiple of 32 (frame %dx%d, res %d)", P.H, P.W, P.Hf, P.Wf, P.res);
+  const void* net_in = nullptr;   // filled per run when identity (frames pointer) -> patched in run()
+  if (!(new_w == P.Wf && new_h == P.Hf && px == 0 && py == 0)) {
+    const size_t es = P.is_f32 ? 4 : 1;
+    P.lb_out = dalloc(static_cast<size_t>(P.B) * P.H * P.W * 3 * es);
+    Op op; op.kind = Op::LETTERBOX; op.name = "letterbox";
+    op.lb = LetterboxParams{};
+    op.lb.in = nullptr; op.lb.out = P.lb_out; op.lb.is_f32 = P.is_f32;
+    op.lb.B = P.B; op.lb.Hin = P.Hf; op.lb.Win = P.Wf; op.lb.Hr = new_h; op.lb.Wr = new_w;
+    op.lb.pad_y = py; op.lb.pad_x = px; op.lb.Hout = P.H; op.lb.Wout = P.W;
+    op.lb.sx = float(double(P.Wf) / double(new_w)); op.lb.sy = float(double(P.Hf) / double(new_h));
+    P.ops.push_back(std::move(op));
+    net_in = P.lb_out;
+  }
+
+  outs.assign(nl, T{});
+  cbl_chunks.assign(nl, {});
+  T image; image.image = true; image.C = 3; image.H = P.H; image.W = P.W;
+  T cur = image;
+  for (int i = 0; i < nl && !rc; ++i) {
+    const Layer& l = S[i];
+    const std::string pfx = "model." + std::to_string(i);
+    auto src = [&](int f) -> const T& { return f == -1 ? outs[i - 1] : outs[f]; };
+    T in = (i == 0) ? image : src(l.f[0]);
+    T out;
+    switch (l.op) {
+      case L_SILENCE: out = image; break;
+      case L_CONV: {
+        if (in.image) {
+          CC_REQUIRE(l.a == 3 && l.k == 3 && l.s == 2, "yolo: unexpected image conv");
+          out = out_for(i, l.b, in.H / 2, in.W / 2);
+          Op op; op.kind = Op::STEM; op.name = pfx;
+          const ConvW& cw = M.convs[pfx];
+          op.stem = StemParams{};
+          op.stem.in = net_in; op.stem.is_f32 = P.is_f32; op.stem.B = P.B; op.stem.H = P.H; op.stem.W = P.W;
+          op.stem.w = cw.wf32; op.stem.bias = cw.bias; op.stem.Cout = cw.cout; op.stem.out = ts(out);
+          P.conv_flops += 2.0 * P.B * (P.H / 2) * (P.W / 2) * cw.cout * 27;
+          P.ops.push_back(std::move(op));
+        } else {
+          out = out_for(i, l.b, l.s == 2 ? in.H / 2 : in.H, l.s == 2 ? in.W / 2 : in.W);
+          conv(pfx, in, out, l.s, CC_ACT_SILU);
+        }
+        break;
+      }
+      case L_ELAN1: {
+        // detection/yolov9.py:65-80: cv1 -> chunk2 -> cv2 -> cv3 -> cat4 -> cv4
+        const int ch1 = l.b, ch2 = l.c, ch3 = l.n;
+        T cat = talloc(ch3, in.H, in.W);
+        conv(pfx + ".cv1", in, slice(cat, 0, ch1), 1, CC_ACT_SILU);
+        conv(pfx + ".cv2", slice(cat, ch1 / 2, ch2), slice(cat, ch1, ch2), 1, CC_ACT_SILU);
+        conv(pfx + ".cv3", slice(cat, ch1, ch2), slice(cat, ch1 + ch2, ch2), 1, CC_ACT_SILU);
+        out = out_for(i, ch1, in.H, in.W);
+        conv(pfx + ".cv4", cat, out, 1, CC_ACT_SILU);
+        break;
+      }
+      case L_ELAN4: {
+        // detection/yolov9.py:107-125
+        const int b = l.b;
+        T cat = talloc(8 * b, in.H, in.W);
+        conv(pfx + ".cv1", in, slice(cat, 0, 4 * b), 1, CC_ACT_SILU);
+        T r1 = repncsp(pfx + ".cv2.0", slice(cat, 2 * b, 2 * b), b, l.n);
+        conv(pfx + ".cv2.1", r1, slice(cat, 4 * b, 2 * b), 1, CC_ACT_SILU);
+        T r2 = repncsp(pfx + ".cv3.0", slice(cat, 4 * b, 2 * b), b, l.n);
+        conv(pfx + ".cv3.1", r2, slice(cat, 6 * b, 2 * b), 1, CC_ACT_SILU);
+        out = out_for(i, l.c, in.H, in.W);
+        conv(pfx + ".cv4", cat, out, 1, CC_ACT_SILU);
+        break;
+      }
+      case L_ADOWN: {
+        // detection/yolov9.py:40-52
+        const int ch = l.a;
+        CC_REQUIRE(in.C == 2 * ch, "yolo: ADown(%d) fed %d channels", ch, in.C);
+        T t1 = talloc(ch, in.H, in.W);
+        simple(Op::AVGPAD, slice(in, 0, ch), t1, "adown.avg");
+        out = out_for(i, 2 * ch, in.H / 2, in.W / 2);
+        conv(pfx + ".cv1", t1, slice(out, 0, ch), 2, CC_ACT_SILU);
+        T t2 = talloc(ch, in.H / 2, in.W / 2);
+        simple(Op::AVGMAX, slice(in, ch, ch), t2, "adown.avgmax");
+        conv(pfx + ".cv2", t2, slice(out, ch, ch), 1, CC_ACT_SILU);
+        break;
+      }
+      case L_ACONV: {
+        // detection/yolov9.py:54-63
+        T t1 = talloc(in.C, in.H, in.W);
+        simple(Op::AVGPAD, in, t1, "aconv.avg");
+        out = out_for(i, l.b, in.H / 2, in.W / 2);
+        conv(pfx + ".cv1", t1, out, 2, CC_ACT_SILU);
+        break;
+      }
+      case L_SPPELAN: {
+        // detection/yolov9.py:134-149
+        const int c1 = l.b;
+        T cat = talloc(4 * c1, in.H, in.W);
+        conv(pfx + ".cv1", in, slice(cat, 0, c1), 1, CC_ACT_SILU);
+        for (int q = 0; q < 3; ++q) simple(Op::MAXPOOL5, slice(cat, q * c1, c1), slice(cat, (q + 1) * c1, c1), "spp.max5");
+        out = out_for(i, l.c, in.H, in.W);
+        conv(pfx + ".cv5", cat, out, 1, CC_ACT_SILU);
+        break;
+      }
+      case L_UPSAMPLE: {
+        out = out_for(i, in.C, in.H * 2, in.W * 2);
+        simple(Op::UPSAMPLE, in, out, "upsample");
+        break;
+      }
+      case L_CONCAT: {
+        if (concat_buf.count(i)) { out = concat_buf[i]; break; }
+        // fallback (a source was already placed elsewhere): explicit copy through 1:1 "upsample"-free path not needed
+        // for the reference graphs; refuse rather than silently mis-route.
+        CC_REQUIRE(false, "yolo: concat %d has no placement", i);
+        break;
+      }
+      case L_CBLINEAR: {
+        // detection/yolov9.py:222-228: bare 1x1 conv, split into chunks
+        out = talloc(outC[i], in.H, in.W);
+        conv(pfx + ".conv", in, out, 1, CC_ACT_NONE);
+        int co = 0;
+        for (int c : l.list) { cbl_chunks[i].push_back(slice(out, co, c)); co += c; }
+        break;
+      }
+      case L_CBFUSE: {
+        // detection/yolov9.py:230-245
+        const T& last = src(l.f.back());
+        out = out_for(i, last.C, last.H, last.W);
+        Op op; op.kind = Op::CBFUSE; op.name = pfx;
+        op.cbf = CBFuseParams{};
+        op.cbf.nsrc = static_cast<int>(l.f.size()) - 1;
+        for (int q = 0; q < op.cbf.nsrc; ++q) {
+          const T& ch = cbl_chunks[l.f[q]][l.list[q]];
+          CC_REQUIRE(ch.C == last.C, "yolo: CBFuse chunk has %d channels, target %d", ch.C, last.C);
+          op.cbf.src[q] = ts(ch);
+        }
+        op.cbf.last = ts(last); op.cbf.out = ts(out);
+        P.ops.push_back(std::move(op));
+        break;
+      }
+      case L_DETECT: {
+        // detection/yolov9.py:157-220 + postprocess :439-458 + scale_boxes :406-421
+        const int d = l.a;
+        Op dec; dec.kind = Op::DECODE; dec.name = "decode";
+        dec.dec = DecodeParams{};
+        int A = 0;
+        for (int q = 0; q < 3; ++q) {
+          const T& x = src(l.f[q]);
+          const std::string hp = pfx;
+          const std::string sq = std::to_string(q);
+          T t0 = talloc(64 + d, x.H, x.W);                     // [box branch 64 | class branch d]
+          conv(hp + ".cv2+cv3." + sq + ".0", x, t0, 1, CC_ACT_SILU);
+          T tb = talloc(64, x.H, x.W), tc = talloc(d, x.H, x.W);
+          conv(hp + ".cv2." + sq + ".1", slice(t0, 0, 64), tb, 1, CC_ACT_SILU);
+          conv(hp + ".cv3." + sq + ".1", slice(t0, 64, d), tc, 1, CC_ACT_SILU);
+          float* bl = static_cast<float*>(dalloc(static_cast<size_t>(P.B) * x.H * x.W * 64 * 4));
+          float* cl = static_cast<float*>(dalloc(static_cast<size_t>(P.B) * x.H * x.W * 80 * 4));
+          T dummy;
+          conv(hp + ".cv2." + sq + ".2", tb, dummy, 1, CC_ACT_NONE, nullptr, bl);
+          conv(hp + ".cv3." + sq + ".2", tc, dummy, 1, CC_ACT_NONE, nullptr, cl);
+          dec.dec.box[q] = bl; dec.dec.cls[q] = cl; dec.dec.h[q] = x.H; dec.dec.w[q] = x.W;
+          dec.dec.stride[q] = float(P.H / x.H);
+          A += x.H * x.W;
+        }
+        P.A = A;
+        P.pred = static_cast<float*>(dalloc(static_cast<size_t>(P.B) * A * 6 * 4));
+        dec.dec.B = P.B; dec.dec.A = A; dec.dec.conf_thr = 0.25f; dec.dec.pred = P.pred; dec.dec.raw = nullptr;
+        P.ops.push_back(std::move(dec));
+        Op po; po.kind = Op::POST; po.name = "postprocess";
+        po.post = PostParams{};
+        po.post.pred = P.pred; po.post.B = P.B; po.post.A = A; po.post.max_det = 300; po.post.iou_thr = 0.45f;
+        const double gain = std::min(double(P.H) / P.Hf, double(P.W) / P.Wf);
+        po.post.gain = float(gain);
+        po.post.pad_x = float((P.W - P.Wf * gain) / 2); po.post.pad_y = float((P.H - P.Hf * gain) / 2);
+        po.post.clip_w = float(P.Wf); po.post.clip_h = float(P.Hf); po.post.do_scale = 1;
+        po.post.out = nullptr;
+        P.ops.push_back(std::move(po));
+        break;
+      }
+    }
+    outs[i] = out;
+  }
+  P.n_launch = static_cast<int>(P.ops.size());
+  P.layer_outs = outs;
+  return rc;
+}
+
+static int plan_run(YoloPlan& P, const void* d_frames, float* d_out, float* d_raw, cudaStream_t st) {
+  for (Op& op : P.ops) {
+    int rc = CC_OK;
+    switch (op.kind) {
+      case Op::GEMM: rc = conv_gemm_launch(op.gemm, st); break;
+      case Op::DIRECT: rc = conv_direct_launch(op.direct, st); break;
+      case Op::AVGPAD: rc = avgpool2_pad_launch(op.s_in, op.s_out, st); break;
+      case Op::AVGMAX: rc = avgmax_pool_launch(op.s_in, op.s_out, st); break;
+      case Op::MAXPOOL5: rc = maxpool5_launch(op.s_in, op.s_out, st); break;
+      case Op::UPSAMPLE: rc = upsample2_launch(op.s_in, op.s_out, st); break;
+      case Op::CBFUSE: rc = cbfuse_launch(op.cbf, st); break;
+      case Op::LETTERBOX: { LetterboxParams q = op.lb; q.in = d_frames; rc = letterbox_launch(q, st); break; }
+      case Op::STEM: { StemParams q = op.stem; if (!q.in) q.in = d_frames; rc = stem_launch(q, st); break; }
+      case Op::DECODE: { DecodeParams q = op.dec; q.raw = d_raw; rc = decode_launch(q, st); break; }
+      case Op::POST: { PostParams q = op.post; q.out = d_out; rc = postprocess_launch(q, st); break; }
+    }
+    if (rc) return rc;
+  }
+  return CC_OK;
+}
+
+}  // namespace cc
+
+using namespace cc;
+
+struct cc_yolo { YoloModel m; };
+
+extern "C" {
+
+int cc_yolo_create(const char* size, int n_tensors, const char* const* names, const float* const* h_data,
+                   const int64_t* numels, cc_yolo** out) {
+  CC_REQUIRE(size && out, "cc_yolo_create: null argument");
+  const int sms = device_sm_count();
+  CC_REQUIRE(sms > 0, "cc_yolo_create: no sm_100 (B200) device");
+  std::unique_ptr<cc_yolo> h(new cc_yolo());
+  YoloModel& M = h->m;
+  M.size = size;
+  M.sms = sms;
+  CC_REQUIRE(build_spec(M.size, &M.spec), "cc_yolo_create: unknown size '%s' (t|s|m|c|e)", size);
+  for (int i = 0; i < n_tensors; ++i) M.host[names[i]] = HostT{h_data[i], static_cast<long long>(numels[i])};
+
+  int rc = CC_OK;
+  auto L = [&](const std::string& key, std::vector<std::string> nm, int cin, std::vector<int> couts, int k, int g = 1,
+               bool stem = false) {
+    if (rc) return;
+    int ct = 0;
+    for (int c : couts) ct += c;
+    const bool dense = tc_ok(cin, ct);   // grouped convs ride the tensor-core kernel as block-diagonal dense
+    rc = M.load_conv(key, nm, cin, couts, k, g, dense || g == 1, stem);
+  };
+  auto repncsp = [&](const std::string& p, int a, int b, int n) {
+    L(p + ".cv1+cv2", {p + ".cv1.conv", p + ".cv2.conv"}, a, {b, b}, 1);
+    L(p + ".cv3", {p + ".cv3.conv"}, a, {a}, 1);
+    for (int i = 0; i < n; ++i) {
+      const std::string q = p + ".m." + std::to_string(i);
+      L(q + ".cv1", {q + ".cv1.conv"}, b, {b}, 3);
+      L(q + ".cv2", {q + ".cv2.conv"}, b, {b}, 3);
+    }
+  };
+  for (size_t i = 0; i < M.spec.size() && !rc; ++i) {
+    const Layer& l = M.spec[i];
+    const std::string p = "model." + std::to_string(i);
+    switch (l.op) {
+      case L_CONV: L(p, {p + ".conv"}, l.a, {l.b}, l.k, 1, l.a == 3); break;
+      case L_ELAN1:
+        L(p + ".cv1", {p + ".cv1.conv"}, l.a, {l.b}, 1);
+        L(p + ".cv2", {p + ".cv2.conv"}, l.c, {l.c}, 3);
+        L(p + ".cv3", {p + ".cv3.conv"}, l.c, {l.c}, 3);
+        L(p + ".cv4", {p + ".cv4.conv"}, l.n, {l.b}, 1);
+        break;
+      case L_ELAN4:
+        L(p + ".cv1", {p + ".cv1.conv"}, l.a, {4 * l.b}, 1);
+        repncsp(p + ".cv2.0", 2 * l.b, l.b, l.n);
+        L(p + ".cv2.1", {p + ".cv2.1.conv"}, 2 * l.b, {2 * l.b}, 3);
+        repncsp(p + ".cv3.0", 2 * l.b, l.b, l.n);
+        L(p + ".cv3.1", {p + ".cv3.1.conv"}, 2 * l.b, {2 * l.b}, 3);
+        L(p + ".cv4", {p + ".cv4.conv"}, 8 * l.b, {l.c}, 1);
+        break;
+      case L_ADOWN:
+        L(p + ".cv1", {p + ".cv1.conv"}, l.a, {l.a}, 3);
+        L(p + ".cv2", {p + ".cv2.conv"}, l.a, {l.a}, 1);
+        break;
+      case L_ACONV: L(p + ".cv1", {p + ".cv1.conv"}, l.a, {l.b}, 3); break;
+      case L_SPPELAN:
+        L(p + ".cv1", {p + ".cv1.conv"}, l.a, {l.b}, 1);
+        L(p + ".cv5", {p + ".cv5.conv"}, 4 * l.b, {l.c}, 1);
+        break;
+      case L_CBLINEAR: {
+        int s = 0;
+        for (int c : l.list) s += c;
+        L(p + ".conv", {p + ".conv"}, l.a, {s}, 1);
+        break;
+      }
+      case L_DETECT:
+        for (int q = 0; q < 3; ++q) {
+          const std::string sq = std::to_string(q);
+          L(p + ".cv2+cv3." + sq + ".0", {p + ".cv2." + sq + ".0.conv", p + ".cv3." + sq + ".0.conv"}, l.list[q], {64, l.a}, 3);
+          L(p + ".cv2." + sq + ".1", {p + ".cv2." + sq + ".1.conv"}, 64, {64}, 3, 4);
+          L(p + ".cv2." + sq + ".2", {p + ".cv2." + sq + ".2"}, 64, {64}, 1, 4);
+          L(p + ".cv3." + sq + ".1", {p + ".cv3." + sq + ".1.conv"}, l.a, {l.a}, 3);
+          L(p + ".cv3." + sq + ".2", {p + ".cv3." + sq + ".2"}, l.a, {80}, 1);
+        }
+        break;
+      default: break;
+    }
+  }
+  M.host.clear();
+  if (rc) return rc;
+  *out = h.release();
+  return CC_OK;
+}
+
+int cc_yolo_destroy(cc_yolo* h) {
+  delete h;
+  return CC_OK;
+}
+
+static int get_plan(cc_yolo* h, int is_f32, int B, int Hf, int Wf, int res, YoloPlan** out) {
+  char key[96];
+  snprintf(key, sizeof(key), "%d,%d,%d,%d,%d", is_f32, B, Hf, Wf, res);
+  auto it = h->m.plans.find(key);
+  if (it == h->m.plans.end()) {
+    std::unique_ptr<YoloPlan> P(new YoloPlan());
+    P->B = B; P->Hf = Hf; P->Wf = Wf; P->res = res; P->is_f32 = is_f32;
+    Builder bld(h->m, *P);
+    int rc = bld.build();
+    if (rc) return rc;
+    it = h->m.plans.emplace(key, std::move(P)).first;
+  }
+  *out = it->second.get();
+  return CC_OK;
+}
+
+int cc_yolo_forward(cc_yolo* h, const void* d_frames, int is_f32, int B, int Hf, int Wf, int res, float* d_out,
+                    float* d_raw, void* stream) {
+  CC_REQUIRE(h && d_frames && d_out && B > 0 && Hf > 0 && Wf > 0 && res > 0, "cc_yolo_forward: bad argument");
+  YoloPlan* P = nullptr;
+  int rc = get_plan(h, is_f32, B, Hf, Wf, res, &P);
+  if (rc) return rc;
+  return plan_run(*P, d_frames, d_out, d_raw, static_cast<cudaStream_t>(stream));
+}
+
+int cc_yolo_plan_info(cc_yolo* h, int is_f32, int B, int Hf, int Wf, int res, int* net_h, int* net_w, int* anchors,
+                      int* launches, double* conv_flops, double* act_bytes) {
+  CC_REQUIRE(h, "cc_yolo_plan_info: null handle");
+  YoloPlan* P = nullptr;
+  int rc = get_plan(h, is_f32, B, Hf, Wf, res, &P);
+  if (rc) return rc;
+  if (net_h) *net_h = P->H;
+  if (net_w) *net_w = P->W;
+  if (anchors) *anchors = P->A;
+  if (launches) *launches = P->n_launch;
+  if (conv_flops) *conv_flops = P->conv_flops;
+  if (act_bytes) *act_bytes = double(P->alloc_bytes);
+  return CC_OK;
+}
+
+// parity tap: copy the output of spec layer `layer` of the cached plan (after a forward) to dense fp32 NHWC
+__global__ void tap_kernel(const __nv_bfloat16* src, int cs, int co, int C, long long npix, float* dst) {
+  const long long total = npix * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long pix = i / C;
+    const int c = static_cast<int>(i % C);
+    dst[i] = __bfloat162float(src[pix * cs + co + c]);
+  }
+}
+
+int cc_yolo_layer_output(cc_yolo* h, int is_f32, int B, int Hf, int Wf, int res, int layer, float* d_dst, int* C,
+                         int* H, int* W, void* stream) {
+  CC_REQUIRE(h, "cc_yolo_layer_output: null handle");
+  YoloPlan* P = nullptr;
+  int rc = get_plan(h, is_f32, B, Hf, Wf, res, &P);
+  if (rc) return rc;
+  CC_REQUIRE(layer >= 0 && layer < static_cast<int>(P->layer_outs.size()), "cc_yolo_layer_output: bad layer %d", layer);
+  const T& t = P->layer_outs[layer];
+  if (C) *C = t.image ? 0 : t.C;
+  if (H) *H = t.H;
+  if (W) *W = t.W;
+  if (!d_dst || t.image || !t.p) return CC_OK;
+  const long long npix = static_cast<long long>(B) * t.H * t.W;
+  tap_kernel<<<148 * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(t.p, t.cs, t.co, t.C, npix, d_dst);
+  CC_CHECK_CUDA(cudaGetLastError());
+  return CC_OK;
+}
+
+// kernel-level taps for the parity tests
+int cc_detect_postprocess(const float* d_pred, int B, int A, int max_det, float iou_thr, int do_scale, float pad_x,
+                          float pad_y, float gain, float clip_w, float clip_h, float* d_out, void* stream) {
+  PostParams p{};
+  p.pred = d_pred; p.B = B; p.A = A; p.max_det = max_det; p.iou_thr = iou_thr;
+  p.do_scale = do_scale; p.pad_x = pad_x; p.pad_y = pad_y; p.gain = gain; p.clip_w = clip_w; p.clip_h = clip_h;
+  p.out = d_out;
+  return postprocess_launch(p, static_cast<cudaStream_t>(stream));
+}
+
+int cc_detect_decode(const float* const* d_box, const float* const* d_cls, const int* hs, const int* ws, int B,
+                     float conf_thr, float* d_pred, float* d_raw, void* stream) {
+  DecodeParams p{};
+  int A = 0;
+  const float strides[3] = {8.f, 16.f, 32.f};
+  for (int q = 0; q < 3; ++q) {
+    p.box[q] = d_box[q]; p.cls[q] = d_cls[q]; p.h[q] = hs[q]; p.w[q] = ws[q]; p.stride[q] = strides[q];
+    A += hs[q] * ws[q];
+  }
+  p.B = B; p.A = A; p.conf_thr = conf_thr; p.pred = d_pred; p.raw = d_raw;
+  return decode_launch(p, static_cast<cudaStream_t>(stream));
+}
+
+int cc_letterbox(const void* d_in, int is_f32, int B, int Hin, int Win, int res, void* d_out, int* out_h, int* out_w,
+                 void* stream) {
+  const double r = std::min(double(res) / Hin, double(res) / Win);
+  const int new_w = int(std::nearbyint(Win * r)), new_h = int(std::nearbyint(Hin * r));
+  double dw = double(((res - new_w) % 32 + 32) % 32) / 2, dh = double(((res - new_h) % 32 + 32) % 32) / 2;
+  const int px = int(std::nearbyint(dw - 0.1)), py = int(std::nearbyint(dh - 0.1));
+  if (out_h) *out_h = new_h + 2 * py;
+  if (out_w) *out_w = new_w + 2 * px;
+  if (!d_out) return CC_OK;   // size query
+  LetterboxParams p{};
+  p.in = d_in; p.out = d_out; p.is_f32 = is_f32; p.B = B; p.Hin = Hin; p.Win = Win; p.Hr = new_h; p.Wr = new_w;
+  p.pad_y = py; p.pad_x = px; p.Hout = new_h + 2 * py; p.Wout = new_w + 2 * px;
+  p.sx = float(double(Win) / double(new_w)); p.sy = float(double(Hin) / double(new_h));
+  return letterbox_launch(p, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -45,6 +45,50 @@ int cc_conv2d(const void* d_in, int N, int Hin, int Win, int in_cs, int in_co, i
               void* d_out, int out_cs, int out_co, int out_f32, int act,
               const void* d_res, int res_cs, int res_co, int impl, int bn, void* stream);
 
+/* ---- YOLOv9 detector (replaces detection/yolov9.py: class YOLOv9, :298-458) ---- */
+typedef struct cc_yolo cc_yolo;
+
+/* size: "t"|"s"|"c"|"e" ("m" has channel counts that are not multiples of 8 and is not supported yet).
+ * Weights: n host fp32 tensors in PyTorch layout, named with the reference's state-dict keys with `.list.`
+ * elided, e.g. "model.0.conv.weight", "model.2.cv2.0.cv1.conv.bias", "model.22.cv2.0.2.weight"
+ * (what safe_load/load_state_dict consume at detection/yolov9.py:372-373).  They are repacked to the kernel
+ * layout and uploaded once; the host pointers are not retained. */
+int cc_yolo_create(const char* size, int n_tensors, const char* const* names, const float* const* h_data,
+                   const int64_t* numels, cc_yolo** out);
+int cc_yolo_destroy(cc_yolo* h);
+
+/* YOLOv9.__call__ (detection/yolov9.py:375-388) for a batch of same-shape frames.
+ * d_frames: [B,Hf,Wf,3] HWC **BGR**, uint8 (is_f32=0, clearcam.py:582) or float32 (is_f32=1, test/run_mot.py:33).
+ * d_out: [B,300,6] fp32 rows [x1,y1,x2,y2,conf,class] in frame pixels, descending conf, suppressed rows all-zero.
+ * d_raw: optional [B,84,A] fp32 tap of the head output (xc,yc,w,h,80 class probs) for parity tests, or NULL.
+ * A plan (buffers, TMA descriptors) is built and cached on the first call for each (dtype,B,Hf,Wf,res) — the
+ * analogue of jit_infer's per-shape TinyJit cache (utils/helpers.py:214-221); later calls only launch kernels. */
+int cc_yolo_forward(cc_yolo* h, const void* d_frames, int is_f32, int B, int Hf, int Wf, int res, float* d_out,
+                    float* d_raw, void* stream);
+/* plan facts: letterboxed net input size, anchors, kernel launches per forward, algorithmic conv FLOPs,
+ * bytes of activation workspace */
+int cc_yolo_plan_info(cc_yolo* h, int is_f32, int B, int Hf, int Wf, int res, int* net_h, int* net_w, int* anchors,
+                      int* launches, double* conv_flops, double* act_bytes);
+
+/* parity tap: after a forward, copy the output of graph layer `layer` (index into the reference's self.model list,
+ * detection/yolov9.py:303-371) to dense fp32 [B,H,W,C].  d_dst == NULL only queries C/H/W (C = 0: no tensor). */
+int cc_yolo_layer_output(cc_yolo* h, int is_f32, int B, int Hf, int Wf, int res, int layer, float* d_dst, int* C,
+                         int* H, int* W, void* stream);
+
+/* kernel-level taps (parity tests) */
+/* postprocess tail (detection/yolov9.py:449-458) [+ scale_boxes :406-421 when do_scale]: d_pred [B,A,6] ->
+ * d_out [B,max_det,6] */
+int cc_detect_postprocess(const float* d_pred, int B, int A, int max_det, float iou_thr, int do_scale, float pad_x,
+                          float pad_y, float gain, float clip_w, float clip_h, float* d_out, void* stream);
+/* DDetect tail (detection/yolov9.py:209-219) + head of postprocess (:440-448): three scales of fp32 logits
+ * d_box[i] [B,h,w,64], d_cls[i] [B,h,w,80] (strides 8,16,32) -> d_pred [B,A,6], optional d_raw [B,84,A] */
+int cc_detect_decode(const float* const* d_box, const float* const* d_cls, const int* hs, const int* ws, int B,
+                     float conf_thr, float* d_pred, float* d_raw, void* stream);
+/* YOLOv9.preprocess (detection/yolov9.py:390-404) + resize (utils/helpers.py:127-131): [B,Hin,Win,3] -> letterboxed
+ * [B,out_h,out_w,3], same dtype.  d_out == NULL only queries the output size. */
+int cc_letterbox(const void* d_in, int is_f32, int B, int Hin, int Win, int res, void* d_out, int* out_h, int* out_w,
+                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

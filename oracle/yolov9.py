@@ -284,7 +284,7 @@ def _detect_fwd(P, q, pfx, xs, d):
     return torch.cat([dbox, torch.sigmoid(cls)], 1)
 
 
-def forward_raw(size: str, P: Dict[str, torch.Tensor], x: torch.Tensor, quant=None) -> torch.Tensor:
+def forward_raw(size: str, P: Dict[str, torch.Tensor], x: torch.Tensor, quant=None, taps: list | None = None) -> torch.Tensor:
     """x: (B,3,H,W) fp32 RGB in [0,1] -> (B,84,A). Mirrors the routing loop of YOLOv9.__call__ (:380-385)."""
     q = _Q(quant)
     spec = build_spec(size)
@@ -347,6 +347,8 @@ def forward_raw(size: str, P: Dict[str, torch.Tensor], x: torch.Tensor, quant=No
         else:
             raise ValueError(op)
         ys.append(cur)
+    if taps is not None:
+        taps.extend(ys)
     return cur
 
 
@@ -479,30 +481,52 @@ def detect(size: str, P, frames, res: int, quant=None, bgr_swap=True) -> torch.T
 
 
 # ------------------------------------------------------------------------------------------------ weights
-def synthetic_weights(size: str, seed: int = 0, calib_hw=(128, 160), cls_bias=-1.5) -> Dict[str, torch.Tensor]:
-    """Seeded weights with the reference's state-dict names.  Every conv is rescaled (LSUV-style, one pass on a
-    fixed seeded image) so its pre-activation std is ~1: all layers stay numerically relevant, which a plain
-    N(0, 2/fan_in) draw does not give through 60+ SiLU layers.  The class head is shifted/scaled so a modest number
-    of anchors pass the 0.25 threshold and overlap (suppression is exercised).  DFL weight = arange(16)."""
+def synthetic_frames(B: int, H: int, W: int, seed: int = 0) -> torch.Tensor:
+    """Seeded uint8 BGR frames with structure (gradient + random filled rectangles + mild noise), so features vary
+    with position the way a camera image's do (uniform noise averages out to position-independent features)."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    yy, xx = torch.meshgrid(torch.linspace(0, 1, H), torch.linspace(0, 1, W), indexing="ij")
+    frames = []
+    for b in range(B):
+        ph = torch.rand(3, generator=g)
+        img = torch.stack([(yy * (0.5 + ph[0]) + xx * ph[1]) % 1.0, (xx * (0.5 + ph[1]) + 0.3 * yy) % 1.0,
+                           (0.5 * yy * xx + ph[2]) % 1.0], -1) * 160 + 40
+        for _ in range(24):
+            rh = int(torch.randint(max(H // 24, 4), max(H // 3, 8), (1,), generator=g))
+            rw = int(torch.randint(max(W // 24, 4), max(W // 3, 8), (1,), generator=g))
+            y0 = int(torch.randint(0, max(H - rh, 1), (1,), generator=g))
+            x0 = int(torch.randint(0, max(W - rw, 1), (1,), generator=g))
+            img[y0:y0 + rh, x0:x0 + rw] = torch.rand(3, generator=g) * 255
+        img = img + torch.randn(H, W, 3, generator=g) * 6
+        frames.append(img.clamp(0, 255).to(torch.uint8))
+    return torch.stack(frames)
+
+
+def synthetic_weights(size: str, seed: int = 0, calib: torch.Tensor | None = None, anchors_frac=0.04,
+                      ) -> Dict[str, torch.Tensor]:
+    """Seeded weights with the reference's state-dict names.
+
+    Every conv is normalised per output channel on one calibration image (data-dependent init: weight /= std_c,
+    bias = -mean_c/std_c + N(0,0.1)), so all ~60 sequential layers stay numerically relevant and position
+    dependent (a plain N(0,2/fan_in) draw collapses to bias-dominated constants).  The class head is shifted so
+    about `anchors_frac` of the anchors pass the 0.25 threshold on the calibration image (top-300 selection and
+    the class-aware suppression are both exercised).  DFL weight = arange(16) as in the reference checkpoint.
+    `calib`: (1,3,H,W) fp32 RGB in [0,1]; default = synthetic_frames(1,320,320,seed) preprocessed."""
     g = torch.Generator().manual_seed(seed)
     P: Dict[str, torch.Tensor] = {}
     table = conv_table(size)
     for name, cin, cout, k, s, grp, act in table:
         fan_in = (cin // grp) * k * k
         P[name + ".weight"] = torch.randn(cout, cin // grp, k, k, generator=g) * (1.0 / fan_in) ** 0.5
-        P[name + ".bias"] = torch.randn(cout, generator=g) * 0.1
+        P[name + ".bias"] = torch.zeros(cout)
     det = max(int(n.split(".")[1]) for n, *_ in table)
     P[f"model.{det}.dfl.conv.weight"] = torch.arange(16, dtype=torch.float32).reshape(1, 16, 1, 1)
-
-    # LSUV pass: hook every conv through a patched F.conv2d-free path = run forward and rescale in order
-    x = torch.rand(1, 3, calib_hw[0], calib_hw[1], generator=g)
+    if calib is None:
+        calib = synthetic_frames(2, 320, 320, seed).flip(-1).permute(0, 3, 1, 2).float() / 255.0
+    # z-quantile such that P(any of 80 classes passes) = anchors_frac
+    p_pair = 1.0 - (1.0 - anchors_frac) ** (1.0 / 80.0)
+    zq = float(torch.distributions.Normal(0.0, 1.0).icdf(torch.tensor(1.0 - p_pair)))
     scaled = set()
-
-    def calibrate():
-        # re-run until every conv has been scaled once (each pass fixes the first unscaled conv encountered
-        # would be O(L^2)); instead intercept conv calls in definition order with a custom _cv.
-        pass
-
     global _cv
     orig_cv = _cv
 
@@ -510,26 +534,34 @@ def synthetic_weights(size: str, seed: int = 0, calib_hw=(128, 160), cls_bias=-1
         if name not in scaled:
             w = P_[name + ".weight"]
             y = F.conv2d(x_, w, None, stride=s, padding=w.shape[-1] // 2, groups=g)
-            sd = float(y.std())
-            if sd > 0:
-                P_[name + ".weight"] = w / sd
+            is_cls = ".cv3." in name and name.endswith(".2")
+            is_dfl = ".cv2." in name and name.endswith(".2")
+            shift = torch.randn(w.shape[0], generator=globals()["_gen"]) * 0.1
+            if is_cls or is_dfl:
+                # heads: centre/scale the logits over the whole map (one scalar pair per head -> still contractive)
+                mu, sd = y.mean(), y.std().clamp(min=1e-6)
+                gain = 0.35 if is_cls else 1.5
+                if is_cls:   # threshold logit(0.25) sits at the z-quantile giving ~anchors_frac passing anchors
+                    shift = shift * 2 + (math.log(0.25 / 0.75) - gain * zq)
+                P_[name + ".weight"] = w * (gain / sd)
+                P_[name + ".bias"] = -mu / sd * gain + shift
+            else:
+                # body: one scalar per conv so the pre-activation RMS is 1 (keeps relative perturbations O(1) per
+                # layer; per-channel whitening would divide by tiny stds and make the net chaotic)
+                rms = y.pow(2).mean().sqrt().clamp(min=1e-6)
+                P_[name + ".weight"] = w / rms
+                P_[name + ".bias"] = shift
             scaled.add(name)
         return orig_cv(P_, q, name, x_, s=s, g=g, act=act, res=res, quant_w=quant_w, store=store)
 
+    globals()["_gen"] = g
     _cv = cv_cal
     try:
         with torch.no_grad():
-            forward_raw(size, P, x)
+            forward_raw(size, P, calib)
     finally:
         _cv = orig_cv
-    # class logits: std 1 around cls_bias -> a few % of anchors above sigmoid^-1(0.25) = -1.1 would be too many;
-    # scale to std 1.2 and shift so ~0.3 % of (anchor,class) pairs pass.
-    for name, cin, cout, k, s, grp, act in table:
-        if ".cv3." in name and name.endswith(".2"):
-            P[name + ".weight"] = P[name + ".weight"] * 1.2
-            P[name + ".bias"] = torch.full((cout,), -4.4) + torch.randn(cout, generator=g) * 0.3
-        if ".cv2." in name and name.endswith(".2"):
-            P[name + ".weight"] = P[name + ".weight"] * 1.5
+        globals().pop("_gen", None)
     return P
 
 
