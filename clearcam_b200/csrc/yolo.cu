@@ -569,9 +569,12 @@ int Builder::build() {
   return rc;
 }
 
-static int plan_run(YoloPlan& P, const void* d_frames, float* d_out, float* d_raw, cudaStream_t st) {
+static int plan_run(YoloPlan& P, const void* d_frames, float* d_out, float* d_raw, cudaStream_t st,
+                    std::vector<cudaEvent_t>* ev = nullptr) {
+  size_t oi = 0;
   for (Op& op : P.ops) {
     int rc = CC_OK;
+    if (ev) cudaEventRecord((*ev)[oi++], st);
     switch (op.kind) {
       case Op::GEMM: rc = conv_gemm_launch(op.gemm, st); break;
       case Op::DIRECT: rc = conv_direct_launch(op.direct, st); break;
@@ -587,7 +590,18 @@ static int plan_run(YoloPlan& P, const void* d_frames, float* d_out, float* d_ra
     }
     if (rc) return rc;
   }
+  if (ev) cudaEventRecord((*ev)[oi], st);
   return CC_OK;
+}
+
+static const char* op_kind_name(Op::Kind k) {
+  switch (k) {
+    case Op::GEMM: return "conv_gemm"; case Op::DIRECT: return "conv_direct"; case Op::AVGPAD: return "avgpool2_pad";
+    case Op::AVGMAX: return "avgmax_pool"; case Op::MAXPOOL5: return "maxpool5"; case Op::UPSAMPLE: return "upsample2";
+    case Op::CBFUSE: return "cbfuse"; case Op::LETTERBOX: return "letterbox"; case Op::STEM: return "stem";
+    case Op::DECODE: return "decode"; case Op::POST: return "postprocess";
+  }
+  return "?";
 }
 
 }  // namespace cc
@@ -724,6 +738,36 @@ int cc_yolo_plan_info(cc_yolo* h, int is_f32, int B, int Hf, int Wf, int res, in
   if (conv_flops) *conv_flops = P->conv_flops;
   if (act_bytes) *act_bytes = double(P->alloc_bytes);
   return CC_OK;
+}
+
+/* Per-op device timing of one forward (CUDA events between launches on `stream`; synchronises at the end).
+ * Fills up to `cap` entries: ms[i], flops[i] (algorithmic, 0 for non-conv ops) and a name pointer valid for the
+ * life of the handle.  Returns the op count through n_ops. */
+int cc_yolo_profile(cc_yolo* h, const void* d_frames, int is_f32, int B, int Hf, int Wf, int res, float* d_out, int cap,
+                    float* ms, double* flops, const char** kinds, const char** names, int* n_ops, void* stream) {
+  CC_REQUIRE(h && d_frames && d_out, "cc_yolo_profile: bad argument");
+  YoloPlan* P = nullptr;
+  int rc = get_plan(h, is_f32, B, Hf, Wf, res, &P);
+  if (rc) return rc;
+  const size_t n = P->ops.size();
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) CC_CHECK_CUDA(cudaEventCreate(&e));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = plan_run(*P, d_frames, d_out, nullptr, st, &ev);
+  if (!rc) {
+    CC_CHECK_CUDA(cudaStreamSynchronize(st));
+    for (size_t i = 0; i < n && static_cast<int>(i) < cap; ++i) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
+      if (ms) ms[i] = t;
+      if (flops) flops[i] = P->ops[i].kind == Op::GEMM ? P->ops[i].gemm.flops : 0.0;
+      if (kinds) kinds[i] = op_kind_name(P->ops[i].kind);
+      if (names) names[i] = P->ops[i].name.c_str();
+    }
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  if (n_ops) *n_ops = static_cast<int>(n);
+  return rc;
 }
 
 // parity tap: copy the output of spec layer `layer` of the cached plan (after a forward) to dense fp32 NHWC

@@ -206,6 +206,21 @@ class YOLOv9:
         return {"net_h": i[0].value, "net_w": i[1].value, "anchors": i[2].value, "launches": i[3].value,
                 "conv_flops": d[0].value, "act_bytes": d[1].value}
 
+    def profile(self, frames):
+        """Per-op device times of one forward: list of dicts {kind, name, ms, flops}."""
+        t = self._as_device_frames(frames)
+        B, Hf, Wf, _ = t.shape
+        out = torch.empty(B, 300, 6, device="cuda", dtype=torch.float32)
+        cap = 1024
+        ms = (ctypes.c_float * cap)()
+        fl = (ctypes.c_double * cap)()
+        kinds = (ctypes.c_char_p * cap)()
+        names = (ctypes.c_char_p * cap)()
+        n = ctypes.c_int()
+        check(lib().cc_yolo_profile(self._h, ptr(t), 1 if t.dtype == torch.float32 else 0, B, Hf, Wf, self.res, ptr(out), cap,
+                                    ms, fl, kinds, names, ctypes.byref(n), stream_ptr()), "cc_yolo_profile")
+        return [{"kind": kinds[i].decode(), "name": names[i].decode(), "ms": ms[i], "flops": fl[i]} for i in range(n.value)]
+
     def layer_output(self, layer: int, B, Hf, Wf, is_f32=False):
         """Parity tap: output of graph layer `layer` of the last forward with this shape, as fp32 (B,C,H,W), or None."""
         c, hh, ww = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()

@@ -1,0 +1,166 @@
+"""GPU parity of the detector path against the CPU oracle (oracle/yolov9.py).
+
+Bars (written here as the prompt requires):
+  * integer / index / selection work (letterbox uint8, top-300 order, suppression, class ids): BIT-EXACT;
+  * fp32 tails (DFL decode, float letterbox, scale_boxes): 2e-5 relative (expf/ordering), boxes 1e-3 px abs;
+  * the bf16 conv stack: compared with the bf16-mirror oracle (same storage format) per layer; any two
+    correct bf16 implementations decorrelate at the 1-ulp (2^-8 relative) level after a few layers because
+    rounding turns sub-ulp differences into whole-ulp flips, so the bar is rel-RMS <= 2.5e-2 per layer and the
+    final detections are compared as sets (same class, box within 3 px, conf within 0.05 for >= 80 % of them).
+    The north-star 1e-3 px bar vs the fp32 oracle is NOT met by bf16 storage (measured numbers in DESIGN.md).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import yolov9 as o
+from clearcam_b200.detection.yolov9 import YOLOv9, postprocess
+from clearcam_b200._lib import lib, check, ptr, stream_ptr
+import ctypes
+
+pytestmark = pytest.mark.gpu
+
+
+# ------------------------------------------------------------------------------------------------ letterbox
+@pytest.mark.parametrize("dtype", [torch.uint8, torch.float32])
+@pytest.mark.parametrize("shape,res", [((270, 480), 320), ((1080, 1920), 640), ((540, 960), 960), ((333, 517), 256)])
+def test_letterbox_bit_exact(shape, res, dtype):
+    fr = o.synthetic_frames(2, shape[0], shape[1], seed=3)
+    if dtype == torch.float32:
+        fr = fr.float() + 0.25
+    want = torch.stack([o.preprocess(f, res) for f in fr])
+    m = YOLOv9.__new__(YOLOv9)
+    m.res = res
+    got = m.preprocess(fr).tensor.cpu()
+    assert got.shape == want.shape and got.dtype == want.dtype
+    assert torch.equal(got, want)
+
+
+# ------------------------------------------------------------------------------------------------ postprocess
+def _rand_raw(B, A, seed, n_pos, ties=True):
+    g = torch.Generator().manual_seed(seed)
+    raw = torch.zeros(B, 84, A)
+    raw[:, 0] = torch.rand(B, A, generator=g) * 600 + 20
+    raw[:, 1] = torch.rand(B, A, generator=g) * 600 + 20
+    raw[:, 2] = torch.rand(B, A, generator=g) * 200 + 1
+    raw[:, 3] = torch.rand(B, A, generator=g) * 200 + 1
+    raw[:, 4:] = torch.rand(B, 80, A, generator=g) * 0.2
+    for b in range(B):
+        idx = torch.randperm(A, generator=g)[:n_pos]
+        cls = torch.randint(0, 6, (n_pos,), generator=g)
+        p = torch.rand(n_pos, generator=g) * 0.7 + 0.26
+        if ties:
+            p = (p * 20).round() / 20 + 0.005          # many exactly equal confidences
+        raw[b, 4 + cls, idx] = p
+        # clusters of near-duplicate boxes so suppression fires
+        raw[b, 0:4, idx[: n_pos // 2]] = raw[b, 0:4, idx[n_pos // 2: 2 * (n_pos // 2)]] + 1.5
+    return raw
+
+
+@pytest.mark.parametrize("A,n_pos", [(8400, 1000), (8400, 120), (5040, 0), (2100, 300), (400, 50)])
+def test_postprocess_bit_exact(A, n_pos):
+    raw = _rand_raw(3, A, seed=A + n_pos, n_pos=n_pos)
+    want = o.postprocess(raw)
+    got = postprocess(raw.cuda()).tensor.cpu()
+    assert torch.equal(got, want), f"max diff {(got - want).abs().max()}"
+
+
+def test_decode_matches_oracle():
+    g = torch.Generator().manual_seed(5)
+    B, hw = 2, [(40, 40), (20, 20), (10, 10)]
+    box = [torch.randn(B, h, w, 64, generator=g) * 2 for h, w in hw]
+    cls = [torch.randn(B, h, w, 80, generator=g) * 2 - 2 for h, w in hw]
+    A = sum(h * w for h, w in hw)
+    # oracle formulas (DDetect tail) on (B,144,A)
+    cat = torch.cat([torch.cat([b, c], -1).reshape(B, -1, 144).permute(0, 2, 1) for b, c in zip(box, cls)], 2)
+    bx, cl = cat.split((64, 80), 1)
+    dist = (bx.reshape(B, 4, 16, A).softmax(2) * torch.arange(16.0).reshape(1, 1, 16, 1)).sum(2)
+    anchors, strides = o.make_anchors(hw)
+    lt, rb = dist.chunk(2, 1)
+    x1y1, x2y2 = anchors.unsqueeze(0) - lt, anchors.unsqueeze(0) + rb
+    want_raw = torch.cat([torch.cat([(x1y1 + x2y2) / 2, x2y2 - x1y1], 1) * strides, torch.sigmoid(cl)], 1)
+    dbox = [b.cuda().contiguous() for b in box]
+    dcls = [c.cuda().contiguous() for c in cls]
+    pred = torch.empty(B, A, 6, device="cuda")
+    raw = torch.empty(B, 84, A, device="cuda")
+    pb = (ctypes.c_void_p * 3)(*[t.data_ptr() for t in dbox])
+    pc = (ctypes.c_void_p * 3)(*[t.data_ptr() for t in dcls])
+    hs = (ctypes.c_int * 3)(*[h for h, _ in hw])
+    ws = (ctypes.c_int * 3)(*[w for _, w in hw])
+    check(lib().cc_detect_decode(pb, pc, hs, ws, B, 0.25, ptr(pred), ptr(raw), stream_ptr()), "decode")
+    raw = raw.cpu()
+    pred = pred.cpu()
+    assert (raw[:, :4] - want_raw[:, :4]).abs().max() < 1e-3          # px
+    assert (raw[:, 4:] - want_raw[:, 4:]).abs().max() < 2e-6
+    probs, ids = raw[:, 4:].max(1)
+    assert torch.equal(pred[..., 5], raw[:, 4:].argmax(1).float())
+    assert torch.equal(pred[..., 4], torch.where(probs >= 0.25, probs, torch.zeros_like(probs)))
+
+
+# ------------------------------------------------------------------------------------------------ full model
+def _setup(size, res, B, H, W, seed, dtype=torch.uint8):
+    fr = o.synthetic_frames(B, H, W, seed=seed)
+    if dtype == torch.float32:
+        fr = fr.float()
+    pre = torch.stack([o.preprocess(f, res) for f in fr])
+    x = pre.flip(-1).permute(0, 3, 1, 2).float() / 255
+    P = o.synthetic_weights(size, seed=seed, calib=x[:2])
+    return fr, x, P
+
+
+def _match(ref, got):
+    """fraction of oracle detections (conf>0) that have a same-class CUDA detection within 3 px / 0.05 conf."""
+    A, Bq = ref[ref[:, 4] > 0], got[got[:, 4] > 0]
+    if len(A) == 0:
+        return 1.0, len(Bq)
+    if len(Bq) == 0:
+        return 0.0, 0
+    d = (A[:, None, :4] - Bq[None, :, :4]).abs().max(-1)[0] + (A[:, None, 5] != Bq[None, :, 5]) * 1e6
+    dc = (A[:, None, 4] - Bq[None, :, 4]).abs()
+    ok = ((d < 3.0) & (dc < 0.05)).any(1)
+    return float(ok.float().mean()), len(Bq)
+
+
+@pytest.mark.parametrize("size,res,B,H,W", [("c", 320, 2, 320, 320), ("e", 256, 2, 256, 256), ("t", 320, 2, 320, 320),
+                                             ("s", 256, 1, 256, 256), ("c", 320, 3, 270, 480), ("c", 640, 8, 640, 640)])
+def test_model_vs_oracle(size, res, B, H, W):
+    fr, x, P = _setup(size, res, B, H, W, seed=7)
+    tq = []
+    with torch.no_grad():
+        raw_q = o.forward_raw(size, P, x, quant="bf16", taps=tq)
+    ref_q = o.detect(size, P, fr, res, quant="bf16")
+    m = YOLOv9(size, res, weights=P)
+    out, raw = m.detect_batch(fr, raw=True)
+    torch.cuda.synchronize()
+    out, raw = out.cpu(), raw.cpu()
+    # (1) per-layer: relative RMS deviation from the bf16-mirror oracle
+    worst = 0.0
+    for i, t in enumerate(tq):
+        if not isinstance(t, torch.Tensor) or t.dim() != 4 or t.shape[1] == 3:
+            continue
+        g = m.layer_output(i, B, H, W)
+        if g is None:
+            continue
+        rel = float((g.cpu() - t).pow(2).mean().sqrt() / t.pow(2).mean().sqrt())
+        worst = max(worst, rel)
+        assert rel < 2.5e-2, f"layer {i}: rel rms {rel}"
+    # (2) head tap: class probabilities and boxes stay close on average
+    assert (raw[:, 4:] - raw_q[:, 4:]).abs().mean() < 1e-3
+    assert (raw[:, :4] - raw_q[:, :4]).abs().mean() < 0.5            # px, mean over all anchors
+    # (3) selection/suppression/scale chain is bit-exact given the SAME head output:
+    want = o.scale_boxes((x.shape[2], x.shape[3]), o.postprocess(raw), (H, W))
+    assert torch.equal(out, want), f"post chain differs: {(out - want).abs().max()}"
+    # (4) final detections as sets
+    fr_ok = [_match(ref_q[b], out[b]) for b in range(B)]
+    frac = np.mean([f for f, _ in fr_ok])
+    assert frac >= 0.8, f"only {frac:.2f} of oracle detections matched ({fr_ok})"
+
+
+def test_call_signature_single_frame():
+    """YOLOv9(size,res)(frame).numpy() -> (300,6) float32 (clearcam.py:582-583)."""
+    fr, x, P = _setup("t", 320, 1, 240, 320, seed=1)
+    m = YOLOv9("t", 320, weights=P)
+    r = m(fr[0].numpy()).numpy()
+    assert r.shape == (300, 6) and r.dtype == np.float32
+    r2 = m(fr[0].float()).numpy()          # float32 frame path (test/run_mot.py:33)
+    assert r2.shape == (300, 6)
