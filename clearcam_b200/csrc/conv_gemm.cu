@@ -19,15 +19,17 @@
 
 namespace cc {
 
-static constexpr int kThreads = 256;
+static constexpr int kThreads = 384;      // w0 TMA, w1 MMA, w2 TMEM alloc, w3 idle, w4..11 epilogue
+static constexpr int kEpiThreads = 256;
 static constexpr int kTileM = 128;
 static constexpr uint32_t kTmemCols = 512;
 static constexpr int kMaxSmem = 232448;  // 227 KB
 
-__device__ __forceinline__ float act_apply(float x, int act) {
-  if (act == ACT_SILU) {
+template <int ACT>
+__device__ __forceinline__ float act_apply(float x) {
+  if (ACT == ACT_SILU) {
     return __fdividef(x, 1.0f + __expf(-x));
-  } else if (act == ACT_GELU_TANH) {
+  } else if (ACT == ACT_GELU_TANH) {
     // 0.5x(1+tanh(sqrt(2/pi)(x+0.044715x^3))), tanh(u) = 1 - 2/(1+exp(2u))   (models/objects.py:125 gelu())
     const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
     const float t = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * u));
@@ -41,6 +43,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+template <int ACT, bool F32>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-B alignment for the 128B-swizzled tiles
@@ -53,14 +56,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   const uint32_t a_bytes = kTileM * row_bytes;
   const uint32_t b_bytes = p.BN * row_bytes;
   const int S = p.stages;
-  const int es = p.out_f32 ? 4 : 2;
-  const int CH = p.out_f32 ? (p.BN < 64 ? p.BN : 64) : (p.BN < 128 ? p.BN : 128);  // columns per staging pass
+  constexpr int es = F32 ? 4 : 2;
+  const int CH = F32 ? (p.BN < 64 ? p.BN : 64) : (p.BN < 128 ? p.BN : 128);  // columns per staging pass
   const uint32_t pitch = CH * es + 16;
 
   uint8_t* sA = smem;
   uint8_t* sB = sA + S * a_bytes;
   uint8_t* sStage = sB + S * b_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + ((kTileM * pitch + 15) & ~15u));
+  float* sBias = reinterpret_cast<float*>(sStage + ((kTileM * pitch + 15) & ~15u));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + p.cout);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + S;
   uint64_t* tfull_bar = bars + 2 * S;
@@ -78,13 +82,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], kEpiThreads);
     }
     fence_mbar_init();
   }
   if (warp == 2) {
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
+  }
+  if (warp >= 4) {  // bias -> smem once per CTA (epilogue reads it as broadcast LDS.128)
+    for (int i = threadIdx.x - 128; i < p.cout; i += kEpiThreads) sBias[i] = p.bias ? __ldg(p.bias + i) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -153,10 +160,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue (4 warps, thread == output row) =====================
-    const int ew = warp & 3;              // TMEM lane quarter this warp may access
-    const int row = ew * 32 + lane;       // row of the 128-pixel tile
-    const int et = threadIdx.x - 128;     // 0..127
+    // ===================== epilogue: 8 warps; warps q and q+4 share TMEM lane quarter q and split the
+    // 16-column chunks between them (even / odd); thread == output row in the register phase ============
+    const int ew = warp & 3;                   // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;          // which chunks of a pass this warp converts
+    const int row = ew * 32 + lane;            // row of the 128-pixel tile
+    const int et = threadIdx.x - 128;          // 0..255
     const int TWm = (1 << p.lTW) - 1, THm = (1 << p.lTH) - 1;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -178,21 +187,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 
       for (int cc0 = 0; cc0 < p.BN; cc0 += CH) {
         const int chn = (p.BN - cc0) < CH ? (p.BN - cc0) : CH;  // columns in this pass (multiple of 16)
-        named_bar_sync(1, 128);                                   // staging buffer free
-        for (int c = 0; c < chn; c += 16) {
+        named_bar_sync(1, kEpiThreads);                          // staging buffer free
+        for (int c = half * 16; c < chn; c += 32) {
           uint32_t v[16];
           tmem_ld16(t_row + cc0 + c, v);
-          tmem_ld_wait();
           const int gcol = nb * p.BN + cc0 + c;  // global output channel of v[0]
+          float bia[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sBias + gcol + 4 * j);
+            bia[4 * j] = b4.x; bia[4 * j + 1] = b4.y; bia[4 * j + 2] = b4.z; bia[4 * j + 3] = b4.w;
+          }
+          tmem_ld_wait();
           float f[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float x = __uint_as_float(v[j]);
-            if (p.bias) x += __ldg(p.bias + gcol + j);
-            f[j] = act_apply(x, p.act);
-          }
+          for (int j = 0; j < 16; ++j) f[j] = act_apply<ACT>(__uint_as_float(v[j]) + bia[j]);
           if (p.res != nullptr && pvalid) {
-            if (p.out_f32) {
+            if (F32) {
               const float4* r4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) +
                                                                  ppix * p.res_cs + p.res_co + gcol);
 #pragma unroll
@@ -209,15 +220,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                  const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&rr[q]);
-                  f[8 * j + 2 * q + 0] += __bfloat162float(h.x);
-                  f[8 * j + 2 * q + 1] += __bfloat162float(h.y);
+                  // bf16 -> fp32 is a 16-bit shift
+                  f[8 * j + 2 * q + 0] += __uint_as_float(rr[q] << 16);
+                  f[8 * j + 2 * q + 1] += __uint_as_float(rr[q] & 0xFFFF0000u);
                 }
               }
             }
           }
           uint8_t* dst = sStage + row * pitch + c * es;
-          if (p.out_f32) {
+          if (F32) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               *reinterpret_cast<float4*>(dst + 16 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
@@ -234,20 +245,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           tc_fence_before();
           mbar_arrive(&tempty_bar[acc]);
         }
-        named_bar_sync(1, 128);  // staging filled
-        // coalesced copy-out: consecutive threads write consecutive 16-B chunks of a pixel's channel run
-        const int cpr = (chn * es) >> 4;  // 16-B chunks per row
-        const int total = kTileM * cpr;
-        for (int i = et; i < total; i += 128) {
-          const int r = i / cpr;
-          const int chk = i - r * cpr;
-          const int qw = w0 + (r & TWm), qh = h0 + ((r >> p.lTW) & THm), qn = n0 + (r >> (p.lTW + p.lTH));
-          if (qw < p.W && qh < p.H && qn < p.N) {
-            const long long pix = (static_cast<long long>(qn) * p.H + qh) * p.W + qw;
-            const uint4 val = *reinterpret_cast<const uint4*>(sStage + r * pitch + chk * 16);
-            uint8_t* g = reinterpret_cast<uint8_t*>(p.out) +
-                         (pix * p.out_cs + p.out_co + nb * p.BN + cc0) * es + chk * 16;
-            *reinterpret_cast<uint4*>(g) = val;
+        named_bar_sync(1, kEpiThreads);  // staging filled
+        // coalesced copy-out, division free: a group of `gsz` (power of two >= chunks per row) lanes owns one row
+        const int cpr = (chn * es) >> 4;  // 16-B chunks per row (2..16)
+        const int lg = cpr > 8 ? 4 : (cpr > 4 ? 3 : (cpr > 2 ? 2 : 1));
+        const int chk = et & ((1 << lg) - 1);
+        const int rstep = kEpiThreads >> lg;
+        if (chk < cpr) {
+          uint8_t* gbase = reinterpret_cast<uint8_t*>(p.out) + static_cast<size_t>(p.out_co + nb * p.BN + cc0) * es + chk * 16;
+          for (int r = et >> lg; r < kTileM; r += rstep) {
+            const int qw = w0 + (r & TWm), qh = h0 + ((r >> p.lTW) & THm), qn = n0 + (r >> (p.lTW + p.lTH));
+            if (qw < p.W && qh < p.H && qn < p.N) {
+              const long long pix = (static_cast<long long>(qn) * p.H + qh) * p.W + qw;
+              const uint4 val = *reinterpret_cast<const uint4*>(sStage + r * pitch + chk * 16);
+              *reinterpret_cast<uint4*>(gbase + pix * p.out_cs * es) = val;
+            }
           }
         }
       }
@@ -392,7 +404,7 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
   const int pitch = CH * es + 16;
   const int staging = (kTileM * pitch + 15) & ~15;
   const int stage_bytes = kTileM * p.BK * 2 + BN * p.BK * 2;
-  const int fixed = 1024 /*align slack*/ + staging + 256 /*barriers*/;
+  const int fixed = 1024 /*align slack*/ + staging + d.Cout * 4 /*bias*/ + 256 /*barriers*/;
   int S = (kMaxSmem - fixed) / stage_bytes;
   if (S > 8) S = 8;
   const int num_kb = p.num_taps * p.chunks_per_tap;
@@ -405,15 +417,28 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
   return CC_OK;
 }
 
-int conv_gemm_launch(const GemmLaunch& L, cudaStream_t stream) {
+template <int ACT, bool F32>
+static int launch_variant(const GemmLaunch& L, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    CC_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CC_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<ACT, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     attr_set = true;
   }
-  conv_gemm_kernel<<<L.grid, kThreads, L.smem_bytes, stream>>>(L.p);
+  conv_gemm_kernel<ACT, F32><<<L.grid, kThreads, L.smem_bytes, stream>>>(L.p);
   CC_CHECK_CUDA(cudaGetLastError());
   return CC_OK;
+}
+
+int conv_gemm_launch(const GemmLaunch& L, cudaStream_t stream) {
+  const bool f32 = L.p.out_f32 != 0;
+  switch (L.p.act) {
+    case ACT_NONE: return f32 ? launch_variant<ACT_NONE, true>(L, stream) : launch_variant<ACT_NONE, false>(L, stream);
+    case ACT_SILU: return f32 ? launch_variant<ACT_SILU, true>(L, stream) : launch_variant<ACT_SILU, false>(L, stream);
+    case ACT_GELU_TANH:
+      return f32 ? launch_variant<ACT_GELU_TANH, true>(L, stream) : launch_variant<ACT_GELU_TANH, false>(L, stream);
+  }
+  set_error("conv_gemm: unknown activation %d", L.p.act);
+  return CC_ERR_INVALID;
 }
 
 }  // namespace cc
