@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       // this thread's pixel (register phase: residual read)
       const int pw = w0 + (row & TWm), ph = h0 + ((row >> p.lTW) & THm), pn = n0 + (row >> (p.lTW + p.lTH));
       const bool pvalid = (pw < p.W) && (ph < p.H) && (pn < p.N);
-      const long long ppix = (static_cast<long long>(pn) * p.H + ph) * p.W + pw;
+      const long long ppix = static_cast<long long>(pn) * p.out_ns + ph * p.W + pw;
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           for (int r = et >> lg; r < kTileM; r += rstep) {
             const int qw = w0 + (r & TWm), qh = h0 + ((r >> p.lTW) & THm), qn = n0 + (r >> (p.lTW + p.lTH));
             if (qw < p.W && qh < p.H && qn < p.N) {
-              const long long pix = (static_cast<long long>(qn) * p.H + qh) * p.W + qw;
+              const long long pix = static_cast<long long>(qn) * p.out_ns + qh * p.W + qw;
               const uint4 val = *reinterpret_cast<const uint4*>(sStage + r * pitch + chk * 16);
               *reinterpret_cast<uint4*>(gbase + pix * p.out_cs * es) = val;
             }
@@ -398,6 +398,7 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
   p.out = d.out; p.out_cs = d.out_cs; p.out_co = d.out_co; p.out_f32 = d.out_f32;
   p.bias = d.bias; p.act = d.act;
   p.res = d.res; p.res_cs = d.res_cs; p.res_co = d.res_co;
+  p.out_ns = d.out_ns > 0 ? d.out_ns : Hout * Wout;
 
   // ---- smem budget -> pipeline depth
   const int CH = d.out_f32 ? (BN < 64 ? BN : 64) : (BN < 128 ? BN : 128);

@@ -38,6 +38,7 @@ struct GemmParams {
   const void* res;                    // residual (same dtype as out) or nullptr
   int32_t res_cs, res_co;
   int32_t cout;
+  int32_t out_ns;                     // pixels per image in the out/residual buffers (default H*W)
 };
 
 struct ConvDesc {
@@ -50,6 +51,7 @@ struct ConvDesc {
   int act;
   const void* res; int res_cs, res_co;
   int bn_override;                         // 0 = heuristic
+  int out_ns;                              // 0 = Hout*Wout; else pixels per image in the out/residual buffers
 };
 
 struct GemmLaunch {

@@ -79,4 +79,16 @@ struct PostParams {
 };
 int postprocess_launch(const PostParams& p, cudaStream_t s);
 
+// ---- CLIP ViT kernels (vit.cu) ----
+int patchify_launch(const float* x, __nv_bfloat16* out, int B, int S, int p, int Kpad, cudaStream_t st);
+int embed_ln_pre_launch(float* x, const float* cls, const float* pos, const float* gamma, const float* beta, int rows, int L,
+                        int W, cudaStream_t st);
+int layernorm_bf16_launch(const float* x, __nv_bfloat16* out, const float* gamma, const float* beta, int rows, int W,
+                          long long row_stride, const int* row_idx, cudaStream_t st);
+int text_embed_launch(const int* ids, const float* tok, const float* pos, float* x, int* eot_row, int B, int L, int W,
+                      int vocab, cudaStream_t st);
+int l2norm_launch(const float* in, float* out, int rows, int D, long long out_stride, float eps, cudaStream_t st);
+int attention_launch(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, int B, int L, int H, int causal, cudaStream_t st);
+int search_scores_launch(const float* index, const float* q, float* scores, int N, int D, int Q, cudaStream_t st);
+
 }  // namespace cc

@@ -94,6 +94,35 @@ int cc_detect_decode(const float* const* d_box, const float* const* d_cls, const
 int cc_letterbox(const void* d_in, int is_f32, int B, int Hin, int Win, int res, void* d_out, int* out_h, int* out_w,
                  void* stream);
 
+/* ---- CLIP image/text encoder (replaces class OpenCLIP, models/objects.py:21-186) ---- */
+typedef struct cc_clip cc_clip;
+typedef struct cc_clip_config {
+  int image_size, patch;                     /* 224, 14 (ViT-L/14 as in the reference) or 224, 32 (ViT-B/32) */
+  int v_width, v_layers, v_heads, v_mlp;     /* vision tower: 1024, 24, 16, 4096 (models/objects.py:50-69) */
+  int embed_dim;                             /* 768 (models/objects.py:55) */
+  int t_width, t_layers, t_heads, t_mlp;     /* text tower: 768, 12, 12, 3072 (models/objects.py:29-47) */
+  int vocab, ctx;                            /* 49408, 77 */
+} cc_clip_config;
+
+/* Weights: host fp32 tensors named with the reference's attribute paths: "visual_conv1.weight", "class_embedding",
+ * "positional_embedding", "ln_pre.weight", "resblocks_img.0.in_proj_weight", "resblocks_img.0.mlp_c_fc.bias",
+ * "ln_post.bias", "proj", "token_embedding.weight", "positional_embedding_text", "resblocks.0.attn_out_proj_weight",
+ * "ln_final.weight", "text_projection" ... (what load_state_dict consumes at models/objects.py:91-92). */
+int cc_clip_create(const cc_clip_config* cfg, int n_tensors, const char* const* names, const float* const* h_data,
+                   const int64_t* numels, cc_clip** out);
+int cc_clip_destroy(cc_clip* h);
+/* OpenCLIP.precompute_embedding (models/objects.py:94-133): d_x [B,3,S,S] fp32 normalised -> L2-normalised
+ * embeddings written to d_out[b*out_row_stride .. +embed_dim) (out_row_stride in floats, 0 = embed_dim; a stride /
+ * offset lets the kernel write straight into this rank's slice of an all-gather buffer). */
+int cc_clip_encode_image(cc_clip* h, const float* d_x, int B, float* d_out, long long out_row_stride, void* stream);
+/* encode_text (models/objects.py:145-186), batched: d_ids [B,ctx] int32 ([49406]+BPE+[49407], zero padded). */
+int cc_clip_encode_text(cc_clip* h, const int32_t* d_ids, int B, float* d_out, long long out_row_stride, void* stream);
+/* per-op device timing of one encode (text != 0: text tower). */
+int cc_clip_profile(cc_clip* h, int text, const void* d_in, int B, float* d_out, int cap, float* ms, double* flops,
+                    const char** names, int* n_ops, double* total_flops, void* stream);
+/* ObjectFinder.search inner loop (models/objects.py:365-376): d_scores[q*N + n] = <d_index[n,:], d_q[q,:]>, fp32. */
+int cc_search_scores(const float* d_index, int N, int D, const float* d_q, int Q, float* d_scores, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
