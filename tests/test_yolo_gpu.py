@@ -164,3 +164,20 @@ def test_call_signature_single_frame():
     assert r.shape == (300, 6) and r.dtype == np.float32
     r2 = m(fr[0].float()).numpy()          # float32 frame path (test/run_mot.py:33)
     assert r2.shape == (300, 6)
+
+
+def test_real_yolov9t_weights_real_frame():
+    """The reference's real YOLOv9-t weights and a real video frame (tests/golden/yolov9t_mot16.npz, made by
+    oracle/make_golden.py): CUDA path vs the fp32 oracle running the current reference code (BGR->RGB swap on)."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "yolov9t_mot16.npz"))
+    P = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w:")}
+    frame = torch.from_numpy(z["frame"])
+    want = o.detect("t", P, frame, 960)[0]
+    m = YOLOv9("t", 960, weights=P)
+    got = m(frame.numpy()).numpy()
+    got = torch.from_numpy(got)
+    n_want, n_got = int((want[:, 4] > 0).sum()), int((got[:, 4] > 0).sum())
+    assert n_want >= 30 and abs(n_want - n_got) <= 3
+    frac, _ = _match(want, got)
+    assert frac >= 0.85, f"matched {frac}"
