@@ -217,6 +217,35 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e = world * B * K / (float(t.item()) / 1000.0)
 
+    # ---- CLIP image tower (the second hot loop): device-resident crops, all ranks, in-place all-gather when N>1
+    clip_res = {}
+    try:
+        from oracle import clip as oc
+        from clearcam_b200.models.objects import OpenCLIP
+        for arch, cb in (("ViT-B/32", 256), ("ViT-L/14", 64)):
+            cfg = oc.CONFIGS[arch]
+            cm = OpenCLIP(weights=oc.synthetic_weights(cfg, seed=0), arch=arch)
+            xs = [oc.synthetic_images(8, cfg.image_size, seed=10 + i)[torch.arange(cb) % 8].cuda() for i in range(3)]
+            for i in range(3):
+                cm.precompute_embedding(xs[i % 3], gather=world > 1)
+            barrier()
+            steps_c = max(3, min(K, 10))
+            e0.record()
+            for i in range(steps_c):
+                cm.precompute_embedding(xs[i % 3], gather=world > 1)
+            e1.record()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+            if dist is not None:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ips = world * cb * steps_c / (float(t.item()) / 1000.0)
+            clip_res[arch] = {"batch_per_gpu": cb, "images_per_s": ips, "tflops": ips * oc.flops_image(cfg) / 1e12,
+                              "gflop_per_image": oc.flops_image(cfg) / 1e9, "all_gather": world > 1}
+            del cm, xs
+            torch.cuda.empty_cache()
+    except Exception as ex:  # the detector line must still be printed
+        clip_res = {"error": repr(ex)}
+
     # ---- roofline of the dominant kernel (rank 0): live per-op CUDA-event timing
     line = None
     if rank == 0:
@@ -252,7 +281,7 @@ def main():
                 "clocks": clocks,
                 "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * HW * HW * 3, "d2h_bytes_per_step": B * 300 * 6 * 4},
                 "gpu_launches": info["launches"] * K,
-                "roofline": roof, "cpu_baseline": cpu}
+                "roofline": roof, "cpu_baseline": cpu, "clip": clip_res}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
