@@ -97,6 +97,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above (barrier init, TMEM alloc, descriptor prefetch, bias -> smem: weights only) overlapped the
+  // tail of the previous kernel; activations of the previous layer are only touched after this point.
+  pdl_wait();
+  pdl_trigger();
 
   const int num_kb = p.num_taps * p.chunks_per_tap;
   const int tiles_wh = p.tiles_w * p.tiles_h;
@@ -415,6 +419,8 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
   L->smem_bytes = fixed + S * stage_bytes;
   L->grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
   L->flops = 2.0 * double(d.N) * Hout * Wout * d.Cout * d.k * d.k * d.Cin;
+  L->bytes = double(d.N) * d.Hin * d.Win * d.Cin * 2 + double(d.N) * Hout * Wout * d.Cout * es * (d.res ? 2 : 1) +
+             double(d.Cout) * d.k * d.k * d.Cin * 2;
   return CC_OK;
 }
 
@@ -425,8 +431,17 @@ static int launch_variant(const GemmLaunch& L, cudaStream_t stream) {
     CC_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<ACT, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     attr_set = true;
   }
-  conv_gemm_kernel<ACT, F32><<<L.grid, kThreads, L.smem_bytes, stream>>>(L.p);
-  CC_CHECK_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(L.grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = L.smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<ACT, F32>, L.p));
   return CC_OK;
 }
 

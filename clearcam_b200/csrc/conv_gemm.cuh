@@ -58,6 +58,7 @@ struct GemmLaunch {
   GemmParams p;
   int grid, smem_bytes;
   double flops;       // 2*M*N*K algorithmic
+  double bytes;       // algorithmic HBM bytes: input slice once + output once (+ residual) + weights once
 };
 
 // Returns 0 on success; <0 and sets cc_last_error otherwise.

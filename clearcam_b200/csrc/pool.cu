@@ -62,7 +62,7 @@ __global__ void avgpool2_pad_kernel(TSlice in, TSlice out) {
       const bf8 a = ld8(at(in, n, h, w, c)), b = ld8(at(in, n, h, w + 1, c));
       const bf8 d = ld8(at(in, n, h + 1, w, c)), e = ld8(at(in, n, h + 1, w + 1, c));
 #pragma unroll
-      for (int i = 0; i < 8; ++i) r.v[i] = (a.v[i] + b.v[i] + d.v[i] + e.v[i]) * 0.25f;
+      for (int i = 0; i < 8; ++i) r.v[i] = ((a.v[i] + b.v[i]) + (d.v[i] + e.v[i])) * 0.25f;
     } else {
 #pragma unroll
       for (int i = 0; i < 8; ++i) r.v[i] = 0.f;
@@ -106,7 +106,7 @@ __global__ void avgmax_pool_kernel(TSlice in, TSlice out) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           // round the average to bf16 first: the reference max-pools the stored avg map
-          const float av = __bfloat162float(__float2bfloat16_rn((a.v[i] + b.v[i] + d.v[i] + e.v[i]) * 0.25f));
+          const float av = __bfloat162float(__float2bfloat16_rn(((a.v[i] + b.v[i]) + (d.v[i] + e.v[i])) * 0.25f));
           m.v[i] = fmaxf(m.v[i], av);
         }
       }

@@ -744,7 +744,7 @@ int cc_yolo_plan_info(cc_yolo* h, int is_f32, int B, int Hf, int Wf, int res, in
  * Fills up to `cap` entries: ms[i], flops[i] (algorithmic, 0 for non-conv ops) and a name pointer valid for the
  * life of the handle.  Returns the op count through n_ops. */
 int cc_yolo_profile(cc_yolo* h, const void* d_frames, int is_f32, int B, int Hf, int Wf, int res, float* d_out, int cap,
-                    float* ms, double* flops, const char** kinds, const char** names, int* n_ops, void* stream) {
+                    float* ms, double* flops, double* bytes, const char** kinds, const char** names, int* n_ops, void* stream) {
   CC_REQUIRE(h && d_frames && d_out, "cc_yolo_profile: bad argument");
   YoloPlan* P = nullptr;
   int rc = get_plan(h, is_f32, B, Hf, Wf, res, &P);
@@ -761,6 +761,7 @@ int cc_yolo_profile(cc_yolo* h, const void* d_frames, int is_f32, int B, int Hf,
       cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
       if (ms) ms[i] = t;
       if (flops) flops[i] = P->ops[i].kind == Op::GEMM ? P->ops[i].gemm.flops : 0.0;
+      if (bytes) bytes[i] = P->ops[i].kind == Op::GEMM ? P->ops[i].gemm.bytes : 0.0;
       if (kinds) kinds[i] = op_kind_name(P->ops[i].kind);
       if (names) names[i] = P->ops[i].name.c_str();
     }

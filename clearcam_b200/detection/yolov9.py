@@ -214,12 +214,14 @@ class YOLOv9:
         cap = 1024
         ms = (ctypes.c_float * cap)()
         fl = (ctypes.c_double * cap)()
+        by = (ctypes.c_double * cap)()
         kinds = (ctypes.c_char_p * cap)()
         names = (ctypes.c_char_p * cap)()
         n = ctypes.c_int()
         check(lib().cc_yolo_profile(self._h, ptr(t), 1 if t.dtype == torch.float32 else 0, B, Hf, Wf, self.res, ptr(out), cap,
-                                    ms, fl, kinds, names, ctypes.byref(n), stream_ptr()), "cc_yolo_profile")
-        return [{"kind": kinds[i].decode(), "name": names[i].decode(), "ms": ms[i], "flops": fl[i]} for i in range(n.value)]
+                                    ms, fl, by, kinds, names, ctypes.byref(n), stream_ptr()), "cc_yolo_profile")
+        return [{"kind": kinds[i].decode(), "name": names[i].decode(), "ms": ms[i], "flops": fl[i], "bytes": by[i]}
+                for i in range(n.value)]
 
     def layer_output(self, layer: int, B, Hf, Wf, is_f32=False):
         """Parity tap: output of graph layer `layer` of the last forward with this shape, as fp32 (B,C,H,W), or None."""

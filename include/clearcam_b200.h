@@ -71,9 +71,10 @@ int cc_yolo_plan_info(cc_yolo* h, int is_f32, int B, int Hf, int Wf, int res, in
                       int* launches, double* conv_flops, double* act_bytes);
 
 /* measurement: per-op device time of one forward (CUDA events between launches on `stream`; synchronises).
- * Up to `cap` entries of ms / algorithmic conv FLOPs / kernel kind / op name (pointers valid while h lives). */
+ * Up to `cap` entries of ms / algorithmic conv FLOPs / algorithmic HBM bytes / kernel kind / op name (pointers valid
+ * while h lives). */
 int cc_yolo_profile(cc_yolo* h, const void* d_frames, int is_f32, int B, int Hf, int Wf, int res, float* d_out, int cap,
-                    float* ms, double* flops, const char** kinds, const char** names, int* n_ops, void* stream);
+                    float* ms, double* flops, double* bytes, const char** kinds, const char** names, int* n_ops, void* stream);
 
 /* parity tap: after a forward, copy the output of graph layer `layer` (index into the reference's self.model list,
  * detection/yolov9.py:303-371) to dense fp32 [B,H,W,C].  d_dst == NULL only queries C/H/W (C = 0: no tensor). */

@@ -15,7 +15,12 @@ for _ in range(3):
     prof = m.profile(frames)
 tot = sum(r["ms"] for r in prof)
 print(f"total {tot:.3f} ms for B={B}  ({B/tot*1000:.0f} fps)")
-print(f"{'#':>3} {'kind':12s} {'name':34s} {'ms':>8s} {'TFLOP/s':>8s} {'%':>5s}")
+print(f"{'#':>3} {'kind':12s} {'name':34s} {'ms':>8s} {'TFLOP/s':>8s} {'GB/s':>7s} {'ideal_ms':>8s} {'gap_ms':>7s}")
+ideal_tot = 0.0
 for i, r in enumerate(prof):
     tf = r["flops"] / r["ms"] / 1e9 if r["ms"] > 0 else 0
-    print(f"{i:3d} {r['kind']:12s} {r['name']:34s} {r['ms']:8.4f} {tf:8.1f} {100*r['ms']/tot:5.1f}")
+    gb = r["bytes"] / r["ms"] / 1e6 if r["ms"] > 0 else 0
+    ideal = max(r["flops"] / 1443e9, r["bytes"] / 6569e6)
+    ideal_tot += ideal
+    print(f"{i:3d} {r['kind']:12s} {r['name']:34s} {r['ms']:8.4f} {tf:8.1f} {gb:7.0f} {ideal:8.4f} {r['ms']-ideal:7.4f}")
+print(f"sum of per-layer ideals (conv_gemm only): {ideal_tot:.3f} ms")
