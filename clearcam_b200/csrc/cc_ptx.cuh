@@ -136,6 +136,18 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t 
   d |= layout << 61;                                                // swizzle mode    [61,64)
   return d;
 }
+// Same, for a 128B-swizzled K-major view whose 8-row groups are `sbo_bytes` apart and whose start may be shifted by
+// whole 128-B rows inside the swizzle atom (halo views): base_offset carries (start >> 7) & 7 when requested.
+__device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t base_offset) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(base_offset & 7) << 49;
+  d |= 2ull << 61;
+  return d;
+}
 // Instruction descriptor for kind::f16: fp32 accumulate, A/B = bf16 (fmt 1) or fp16 (fmt 0), both K-major.
 __host__ __device__ __forceinline__ uint32_t umma_idesc_f16(uint32_t M, uint32_t N, uint32_t ab_fmt) {
   return (1u << 4) | (ab_fmt << 7) | (ab_fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);

@@ -15,6 +15,7 @@
 #include "conv_gemm.cuh"
 #include "cc_common.h"
 #include "cc_ptx.cuh"
+#include <stdlib.h>
 #include <string.h>
 
 namespace cc {
@@ -60,8 +61,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   const int CH = F32 ? (p.BN < 64 ? p.BN : 64) : (p.BN < 128 ? p.BN : 128);  // columns per staging pass
   const uint32_t pitch = CH * es + 16;
 
+  const uint32_t a_region = p.halo ? 2u * p.halo_bytes : S * a_bytes;   // halo mode: 2 halo stages, S = B stages
   uint8_t* sA = smem;
-  uint8_t* sB = sA + S * a_bytes;
+  uint8_t* sB = sA + a_region;
   uint8_t* sStage = sB + S * b_bytes;
   float* sBias = reinterpret_cast<float*>(sStage + ((kTileM * pitch + 15) & ~15u));
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + p.cout);
@@ -69,7 +71,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   uint64_t* empty_bar = bars + S;
   uint64_t* tfull_bar = bars + 2 * S;
   uint64_t* tempty_bar = bars + 2 * S + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+  uint64_t* afull_bar = bars + 2 * S + 4;     // halo mode
+  uint64_t* aempty_bar = bars + 2 * S + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 8);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
@@ -83,6 +87,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], kEpiThreads);
+      mbar_init(&afull_bar[i], 1);
+      mbar_init(&aempty_bar[i], 1);
     }
     fence_mbar_init();
   }
@@ -110,6 +116,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
+      if (p.halo) {
+        int sa = 0;
+        uint32_t pa = 0;
+        const int cin = p.chunks_per_tap * 64;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+          const int nb = tile % p.n_blocks;
+          const int m = tile / p.n_blocks;
+          const int w0 = (m % p.tiles_w) << 3;
+          const int h0 = ((m / p.tiles_w) % p.tiles_h) << p.lTH;
+          const int n0 = (m / tiles_wh) << p.lTN;
+          for (int ch = 0; ch < p.chunks_per_tap; ++ch) {
+            mbar_wait(&aempty_bar[sa], pa ^ 1);
+            mbar_arrive_expect_tx(&afull_bar[sa], p.halo_bytes);
+            tma_load_5d(sA + sa * p.halo_bytes, &p.tmA, &afull_bar[sa], ch * 64, w0 - 1, n0, h0 - 1, 0);
+            if (++sa == 2) { sa = 0; pa ^= 1; }
+            for (int t = 0; t < 9; ++t) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              mbar_arrive_expect_tx(&full_bar[stage], b_bytes);
+              tma_load_2d(sB + stage * b_bytes, &p.tmB, &full_bar[stage], t * cin + ch * 64, nb * p.BN);
+              if (++stage == S) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      } else
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int nb = tile % p.n_blocks;
         const int m = tile / p.n_blocks;
@@ -142,6 +172,37 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      if (p.halo) {
+        int sa = 0;
+        uint32_t pa = 0;
+        const uint32_t tn16 = 16u << p.lTN;  // halo pixels per halo row block (TN images x 16 px)
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+          mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * 256;
+          for (int ch = 0; ch < p.chunks_per_tap; ++ch) {
+            mbar_wait(&afull_bar[sa], pa);
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(sA + sa * p.halo_bytes);
+            for (int t = 0; t < 9; ++t) {
+              const uint32_t r = t / 3, sx = t - 3 * r;
+              mbar_wait(&full_bar[stage], phase);
+              tc_fence_after();
+              const uint64_t adesc = umma_smem_desc_sw128(a_base + (r * tn16 + sx) * 128u, 2048u, p.halo_bo ? sx : 0u);
+              const uint64_t bdesc = umma_smem_desc(smem_u32(sB + stage * b_bytes), 128);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ch | t | k) != 0 ? 1u : 0u);
+              umma_commit(&empty_bar[stage]);
+              if (++stage == S) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(&aempty_bar[sa]);
+            if (++sa == 2) { sa = 0; pa ^= 1; }
+          }
+          umma_commit(&tfull_bar[acc]);
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+        }
+      } else
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -181,7 +242,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       const int n0 = (m / tiles_wh) << p.lTN;
 
       // this thread's pixel (register phase: residual read)
-      const int pw = w0 + (row & TWm), ph = h0 + ((row >> p.lTW) & THm), pn = n0 + (row >> (p.lTW + p.lTH));
+      int pw, ph, pn;
+      if (p.halo) { pw = w0 + (row & 7); pn = n0 + ((row >> 3) & ((1 << p.lTN) - 1)); ph = h0 + (row >> (3 + p.lTN)); }
+      else { pw = w0 + (row & TWm); ph = h0 + ((row >> p.lTW) & THm); pn = n0 + (row >> (p.lTW + p.lTH)); }
       const bool pvalid = (pw < p.W) && (ph < p.H) && (pn < p.N);
       const long long ppix = static_cast<long long>(pn) * p.out_ns + ph * p.W + pw;
 
@@ -258,7 +321,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         if (chk < cpr) {
           uint8_t* gbase = reinterpret_cast<uint8_t*>(p.out) + static_cast<size_t>(p.out_co + nb * p.BN + cc0) * es + chk * 16;
           for (int r = et >> lg; r < kTileM; r += rstep) {
-            const int qw = w0 + (r & TWm), qh = h0 + ((r >> p.lTW) & THm), qn = n0 + (r >> (p.lTW + p.lTH));
+            int qw, qh, qn;
+            if (p.halo) { qw = w0 + (r & 7); qn = n0 + ((r >> 3) & ((1 << p.lTN) - 1)); qh = h0 + (r >> (3 + p.lTN)); }
+            else { qw = w0 + (r & TWm); qh = h0 + ((r >> p.lTW) & THm); qn = n0 + (r >> (p.lTW + p.lTH)); }
             if (qw < p.W && qh < p.H && qn < p.N) {
               const long long pix = static_cast<long long>(qn) * p.out_ns + qh * p.W + qw;
               const uint4 val = *reinterpret_cast<const uint4*>(sStage + r * pitch + chk * 16);
@@ -339,6 +404,22 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
       if (eff > best_eff) { best_eff = eff; best[0] = lw; best[1] = lh; best[2] = ln; }
     }
   p.lTW = best[0]; p.lTH = best[1]; p.lTN = best[2];
+  // halo mainloop for 3x3 stride-1 convs with 64-channel chunks: tile = 8 px wide x (TH rows x TN images), TH*TN = 16
+  static const int halo_env = getenv("CC_HALO") ? atoi(getenv("CC_HALO")) : 1;
+  static const int halo_bo_env = getenv("CC_HALO_BO") ? atoi(getenv("CC_HALO_BO")) : 0;
+  p.halo = (halo_env && d.k == 3 && d.stride == 1 && d.Cin % 64 == 0) ? 1 : 0;
+  p.halo_bo = halo_bo_env;
+  if (p.halo) {
+    double be = -1;
+    for (int lh = 0; lh <= 4; ++lh) {
+      const int th = 1 << lh, tn = 16 >> lh;
+      const double cover = double((Hout + th - 1) / th * th) * ((d.N + tn - 1) / tn * tn);
+      const double eff = double(Hout) * d.N / cover + 1e-6 * lh;   // ties: taller tiles (fewer halo rows per output row)
+      if (eff > be) { be = eff; p.lTH = lh; p.lTN = 4 - lh; }
+    }
+    p.lTW = 3;
+    p.halo_bytes = 64 * 16 * (1 << p.lTN) * ((1 << p.lTH) + 2) * 2;
+  }
   const int TW = 1 << p.lTW, TH = 1 << p.lTH, TN = 1 << p.lTN;
   p.tiles_w = (Wout + TW - 1) / TW;
   p.tiles_h = (Hout + TH - 1) / TH;
@@ -371,7 +452,12 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
     cuuint64_t dims[5], strides[4];
     cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
     const cuuint64_t px = cuuint64_t(d.in_cs) * 2;  // bytes per pixel
-    if (!p.s2) {
+    if (p.halo) {
+      // (C, W, N, H): the box [64 ch][16 px][TN images][TH+2 rows] lands in smem as [row][image][pixel][128 B]
+      dims[0] = d.Cin; dims[1] = d.Win; dims[2] = d.N; dims[3] = d.Hin; dims[4] = 1;
+      strides[0] = px; strides[1] = px * d.Win * d.Hin; strides[2] = px * d.Win; strides[3] = px * d.Win * d.Hin * d.N;
+      box[0] = 64; box[1] = 16; box[2] = TN; box[3] = TH + 2; box[4] = 1;
+    } else if (!p.s2) {
       dims[0] = d.Cin; dims[1] = d.Win; dims[2] = d.Hin; dims[3] = d.N; dims[4] = 1;
       strides[0] = px; strides[1] = px * d.Win; strides[2] = px * d.Win * d.Hin; strides[3] = px * d.Win * d.Hin * d.N;
       box[0] = p.BK; box[1] = TW; box[2] = TH; box[3] = TN; box[4] = 1;
@@ -410,13 +496,25 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
   const int staging = (kTileM * pitch + 15) & ~15;
   const int stage_bytes = kTileM * p.BK * 2 + BN * p.BK * 2;
   const int fixed = 1024 /*align slack*/ + staging + d.Cout * 4 /*bias*/ + 256 /*barriers*/;
-  int S = (kMaxSmem - fixed) / stage_bytes;
-  if (S > 8) S = 8;
-  const int num_kb = p.num_taps * p.chunks_per_tap;
-  if (S > num_kb + 1 && num_kb >= 2) S = num_kb + 1;  // no point in more stages than k-blocks (+1 for the next tile)
-  CC_REQUIRE(S >= 2, "conv_gemm: tile does not fit shared memory (BN=%d BK=%d)", BN, p.BK);
+  int S;
+  if (p.halo) {
+    const int b_bytes = BN * 128;
+    S = (kMaxSmem - fixed - 2 * p.halo_bytes) / b_bytes;
+    if (S > 8) S = 8;
+    if (S < 3) {   // does not fit: fall back to the per-tap mainloop
+      set_error("conv_gemm: halo tile does not fit (BN=%d halo=%d B)", BN, p.halo_bytes);
+      return CC_ERR_INVALID;
+    }
+    L->smem_bytes = fixed + 2 * p.halo_bytes + S * b_bytes;
+  } else {
+    S = (kMaxSmem - fixed) / stage_bytes;
+    if (S > 8) S = 8;
+    const int num_kb = p.num_taps * p.chunks_per_tap;
+    if (S > num_kb + 1 && num_kb >= 2) S = num_kb + 1;  // no point in more stages than k-blocks (+1 for the next tile)
+    CC_REQUIRE(S >= 2, "conv_gemm: tile does not fit shared memory (BN=%d BK=%d)", BN, p.BK);
+    L->smem_bytes = fixed + S * stage_bytes;
+  }
   p.stages = S;
-  L->smem_bytes = fixed + S * stage_bytes;
   L->grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
   L->flops = 2.0 * double(d.N) * Hout * Wout * d.Cout * d.k * d.k * d.Cin;
   L->bytes = double(d.N) * d.Hin * d.Win * d.Cin * 2 + double(d.N) * Hout * Wout * d.Cout * es * (d.res ? 2 : 1) +

@@ -39,6 +39,9 @@ struct GemmParams {
   int32_t res_cs, res_co;
   int32_t cout;
   int32_t out_ns;                     // pixels per image in the out/residual buffers (default H*W)
+  // halo mainloop (3x3 stride-1, Cin % 64 == 0): one TMA load of the (TH+2) x 16-pixel halo per 64-channel chunk,
+  // the nine taps are shifted shared-memory descriptor views of it
+  int32_t halo, halo_bytes, halo_bo;  // enabled / bytes per halo stage / descriptor base_offset mode
 };
 
 struct ConvDesc {
