@@ -29,7 +29,11 @@ static constexpr int kMaxSmem = 232448;  // 227 KB
 template <int ACT>
 __device__ __forceinline__ float act_apply(float x) {
   if (ACT == ACT_SILU) {
-    return __fdividef(x, 1.0f + __expf(-x));
+    // x * 1/(1 + 2^(-x*log2e)) with the two raw MUFU approximations (no range fix-up branches)
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return x * r;
   } else if (ACT == ACT_GELU_TANH) {
     // 0.5x(1+tanh(sqrt(2/pi)(x+0.044715x^3))), tanh(u) = 1 - 2/(1+exp(2u))   (models/objects.py:125 gelu())
     const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
@@ -59,13 +63,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   const int S = p.stages;
   constexpr int es = F32 ? 4 : 2;
   const int CH = F32 ? (p.BN < 64 ? p.BN : 64) : (p.BN < 128 ? p.BN : 128);  // columns per staging pass
-  const uint32_t pitch = CH * es + 16;
+  const uint32_t pitch = p.tma_store ? CH * es : CH * es + 16;
+  const uint32_t stg_bytes = (kTileM * pitch + 15) & ~15u;           // one staging buffer
 
   const uint32_t a_region = p.halo ? 2u * p.halo_bytes : S * a_bytes;   // halo mode: 2 halo stages, S = B stages
   uint8_t* sA = smem;
   uint8_t* sB = sA + a_region;
   uint8_t* sStage = sB + S * b_bytes;
-  float* sBias = reinterpret_cast<float*>(sStage + ((kTileM * pitch + 15) & ~15u));
+  float* sBias = reinterpret_cast<float*>(sStage + stg_bytes * (p.tma_store ? p.stg_bufs : 1));
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + p.cout);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + S;
@@ -78,6 +83,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
+    if (p.tma_store) tma_prefetch_desc(&p.tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < S; ++i) {
@@ -234,6 +240,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const int TWm = (1 << p.lTW) - 1, THm = (1 << p.lTH) - 1;
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t pass_ctr = 0;   // staging passes issued so far (TMA-store double buffering)
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int nb = tile % p.n_blocks;
       const int m = tile / p.n_blocks;
@@ -254,6 +261,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 
       for (int cc0 = 0; cc0 < p.BN; cc0 += CH) {
         const int chn = (p.BN - cc0) < CH ? (p.BN - cc0) : CH;  // columns in this pass (multiple of 16)
+        uint8_t* sbuf = sStage;
+        if (p.tma_store) {
+          if (p.stg_bufs == 2) sbuf += (pass_ctr & 1) * stg_bytes;
+          if (et == 0) {  // the buffer about to be overwritten must have been read by its TMA store
+            if (p.stg_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+          }
+        }
         named_bar_sync(1, kEpiThreads);                          // staging buffer free
         for (int c = half * 16; c < chn; c += 32) {
           uint32_t v[16];
@@ -294,6 +308,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
               }
             }
           }
+          if (p.tma_store) {
+            // 128-B rows, 16-B chunk j of row r at slot j ^ (r & 7) (the layout a SWIZZLE_128B TMA store reads);
+            // sub-tiles of 128 B x 128 rows follow each other
+            const uint32_t boff = c * es;                       // byte offset of this 16-column group in the pass row
+            uint8_t* sub = sbuf + (boff >> 7) * (kTileM * 128) + row * 128;
+            const uint32_t ch0 = (boff & 127) >> 4;
+            if (F32) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<float4*>(sub + (((ch0 + j) ^ (row & 7)) << 4)) =
+                    make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 2; ++j)
+                *reinterpret_cast<uint4*>(sub + (((ch0 + j) ^ (row & 7)) << 4)) =
+                    make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                               pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+            }
+          } else {
           uint8_t* dst = sStage + row * pitch + c * es;
           if (F32) {
 #pragma unroll
@@ -306,11 +339,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                   make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
                              pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
           }
+          }
         }
         if (cc0 + CH >= p.BN) {
           // all TMEM reads of this accumulator done -> hand it back to the MMA warp
           tc_fence_before();
           mbar_arrive(&tempty_bar[acc]);
+        }
+        if (p.tma_store) {
+          fence_proxy_async_smem();        // generic-proxy smem writes -> visible to the TMA (async proxy)
+          named_bar_sync(1, kEpiThreads);  // staging filled
+          if (et == 0) {
+            const int nsub = (chn * es) >> 7;
+            const int col0 = nb * p.BN + cc0;
+            for (int j = 0; j < nsub; ++j) {
+              const int cc = col0 + j * (128 / es);
+              if (p.halo) tma_store_5d(&p.tmC, sbuf + j * (kTileM * 128), cc, w0, n0, h0, 0);
+              else tma_store_5d(&p.tmC, sbuf + j * (kTileM * 128), cc, w0, h0, n0, 0);
+            }
+            tma_store_commit();
+          }
+          ++pass_ctr;
+          continue;
         }
         named_bar_sync(1, kEpiThreads);  // staging filled
         // coalesced copy-out, division free: a group of `gsz` (power of two >= chunks per row) lanes owns one row
@@ -337,6 +387,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
   }
 
+  if (p.tma_store && threadIdx.x == 128) tma_store_wait_all();   // all bulk stores of this CTA have landed before it retires
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -492,8 +543,36 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
 
   // ---- smem budget -> pipeline depth
   const int CH = d.out_f32 ? (BN < 64 ? BN : 64) : (BN < 128 ? BN : 128);
-  const int pitch = CH * es + 16;
-  const int staging = (kTileM * pitch + 15) & ~15;
+  static const int tmas_env = getenv("CC_TMASTORE") ? atoi(getenv("CC_TMASTORE")) : 1;
+  p.tma_store = (tmas_env && (BN * es) % 128 == 0) ? 1 : 0;
+  p.stg_bufs = 1;
+  if (p.tma_store) {
+    // double-buffer the staging when the pipeline still gets >= 4 stages (per-tap mode) / 3 B stages (halo mode)
+    const int one = kTileM * CH * es;
+    const int stage_b = p.halo ? BN * 128 : kTileM * p.BK * 2 + BN * p.BK * 2;
+    const int other = 1024 + d.Cout * 4 + 256 + (p.halo ? 2 * p.halo_bytes : 0);
+    if ((kMaxSmem - other - 2 * one) / stage_b >= (p.halo ? 3 : 4)) p.stg_bufs = 2;
+    void* base = reinterpret_cast<uint8_t*>(d.out) + size_t(d.out_co) * es;
+    cuuint64_t dims[5], strides[4];
+    cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
+    const cuuint64_t px = cuuint64_t(d.out_cs) * es;
+    const cuuint64_t img = px * cuuint64_t(p.out_ns);
+    if (p.halo) {
+      dims[0] = d.Cout; dims[1] = Wout; dims[2] = d.N; dims[3] = Hout; dims[4] = 1;
+      strides[0] = px; strides[1] = img; strides[2] = px * Wout; strides[3] = img * d.N;
+      box[0] = 128 / es; box[1] = 8; box[2] = TN; box[3] = TH; box[4] = 1;
+    } else {
+      dims[0] = d.Cout; dims[1] = Wout; dims[2] = Hout; dims[3] = d.N; dims[4] = 1;
+      strides[0] = px; strides[1] = px * Wout; strides[2] = img; strides[3] = img * d.N;
+      box[0] = 128 / es; box[1] = TW; box[2] = TH; box[3] = TN; box[4] = 1;
+    }
+    CUresult r = enc(&p.tmC, d.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CC_REQUIRE(r == CUDA_SUCCESS, "conv_gemm: cuTensorMapEncodeTiled(C) failed: %d", int(r));
+  }
+  const int pitch = p.tma_store ? CH * es : CH * es + 16;
+  const int staging = ((kTileM * pitch + 15) & ~15) * (p.tma_store ? p.stg_bufs : 1);
   const int stage_bytes = kTileM * p.BK * 2 + BN * p.BK * 2;
   const int fixed = 1024 /*align slack*/ + staging + d.Cout * 4 /*bias*/ + 256 /*barriers*/;
   int S;

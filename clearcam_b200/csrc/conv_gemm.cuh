@@ -20,6 +20,7 @@ enum Act : int32_t { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU_TANH = 2 };
 struct GemmParams {
   CUtensorMap tmA;  // 5-D view of the NHWC activation (see conv_gemm.cu)
   CUtensorMap tmB;  // 2-D [Cout][Ktot] weights
+  CUtensorMap tmC;  // 5-D view of the NHWC output slice (TMA-store epilogue)
   int32_t tap[9][4];  // per filter tap: delta on dims 0..3 of the A view
   int32_t num_taps, chunks_per_tap, BK, BN;
   int32_t n_blocks;                   // Cout / BN
@@ -42,6 +43,7 @@ struct GemmParams {
   // halo mainloop (3x3 stride-1, Cin % 64 == 0): one TMA load of the (TH+2) x 16-pixel halo per 64-channel chunk,
   // the nine taps are shifted shared-memory descriptor views of it
   int32_t halo, halo_bytes, halo_bo;  // enabled / bytes per halo stage / descriptor base_offset mode
+  int32_t tma_store, stg_bufs;        // epilogue stores through TMA from 128B-swizzled staging (1 or 2 buffers)
 };
 
 struct ConvDesc {
