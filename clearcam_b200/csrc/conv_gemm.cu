@@ -20,8 +20,12 @@
 
 namespace cc {
 
-static constexpr int kThreads = 384;      // w0 TMA, w1 MMA, w2 TMEM alloc, w3 idle, w4..11 epilogue
-static constexpr int kEpiThreads = 256;
+#ifndef CC_EPI_WARPS
+#define CC_EPI_WARPS 16
+#endif
+static constexpr int kEpiThreads = 32 * CC_EPI_WARPS;   // epilogue warps (multiple of 4: one per TMEM lane quarter)
+static constexpr int kThreads = 128 + kEpiThreads;      // w0 TMA, w1 MMA, w2 TMEM alloc, w3 idle, w4.. epilogue
+static constexpr int kColGroups = CC_EPI_WARPS / 4;     // warps sharing a lane quarter split the 16-column chunks
 static constexpr int kTileM = 128;
 static constexpr uint32_t kTmemCols = 512;
 static constexpr int kMaxSmem = 232448;  // 227 KB
@@ -69,7 +73,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   const uint32_t a_region = p.halo ? 2u * p.halo_bytes : S * a_bytes;   // halo mode: 2 halo stages, S = B stages
   uint8_t* sA = smem;
   uint8_t* sB = sA + a_region;
-  uint8_t* sStage = sB + S * b_bytes;
+  const int num_kb_all = p.num_taps * p.chunks_per_tap;
+  // resident-B mode: sB holds ALL k-blocks of the weights (loaded once); the ring then carries A only
+  uint8_t* sStage = sB + (p.b_res ? num_kb_all : S) * b_bytes;
   float* sBias = reinterpret_cast<float*>(sStage + stg_bytes * (p.tma_store ? p.stg_bufs : 1));
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + p.cout);
   uint64_t* full_bar = bars;
@@ -78,7 +84,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   uint64_t* tempty_bar = bars + 2 * S + 2;
   uint64_t* afull_bar = bars + 2 * S + 4;     // halo mode
   uint64_t* aempty_bar = bars + 2 * S + 6;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 8);
+  uint64_t* bres_bar = bars + 2 * S + 8;      // resident-B mode
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 9);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
@@ -96,6 +103,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       mbar_init(&afull_bar[i], 1);
       mbar_init(&aempty_bar[i], 1);
     }
+    mbar_init(bres_bar, 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -122,6 +130,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
+      if (p.b_res) {   // weights are not produced by the previous kernel: may be issued before/after pdl_wait alike
+        mbar_arrive_expect_tx(bres_bar, num_kb_all * b_bytes);
+        for (int kb = 0; kb < num_kb_all; ++kb) tma_load_2d(sB + kb * b_bytes, &p.tmB, bres_bar, kb * p.BK, 0);
+      }
       if (p.halo) {
         int sa = 0;
         uint32_t pa = 0;
@@ -137,6 +149,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             mbar_arrive_expect_tx(&afull_bar[sa], p.halo_bytes);
             tma_load_5d(sA + sa * p.halo_bytes, &p.tmA, &afull_bar[sa], ch * 64, w0 - 1, n0, h0 - 1, 0);
             if (++sa == 2) { sa = 0; pa ^= 1; }
+            if (!p.b_res)
             for (int t = 0; t < 9; ++t) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
               mbar_arrive_expect_tx(&full_bar[stage], b_bytes);
@@ -161,9 +174,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           const int c4 = p.s2 ? n0 : 0;
           for (int ch = 0; ch < p.chunks_per_tap; ++ch, ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+            mbar_arrive_expect_tx(&full_bar[stage], p.b_res ? a_bytes : a_bytes + b_bytes);
             tma_load_5d(sA + stage * a_bytes, &p.tmA, &full_bar[stage], c_base + ch * p.BK, c1, c2, c3, c4);
-            tma_load_2d(sB + stage * b_bytes, &p.tmB, &full_bar[stage], kb * p.BK, nb * p.BN);
+            if (!p.b_res) tma_load_2d(sB + stage * b_bytes, &p.tmB, &full_bar[stage], kb * p.BK, nb * p.BN);
             if (++stage == S) { stage = 0; phase ^= 1; }
           }
         }
@@ -178,6 +191,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      if (p.b_res) { mbar_wait(bres_bar, 0); tc_fence_after(); }
       if (p.halo) {
         int sa = 0;
         uint32_t pa = 0;
@@ -192,9 +206,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             const uint32_t a_base = smem_u32(sA + sa * p.halo_bytes);
             for (int t = 0; t < 9; ++t) {
               const uint32_t r = t / 3, sx = t - 3 * r;
+              const uint64_t adesc = umma_smem_desc_sw128(a_base + (r * tn16 + sx) * 128u, 2048u, p.halo_bo ? sx : 0u);
+              if (p.b_res) {
+                const uint64_t bdesc = umma_smem_desc(smem_u32(sB + (t * p.chunks_per_tap + ch) * b_bytes), 128);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ch | t | k) != 0 ? 1u : 0u);
+                continue;
+              }
               mbar_wait(&full_bar[stage], phase);
               tc_fence_after();
-              const uint64_t adesc = umma_smem_desc_sw128(a_base + (r * tn16 + sx) * 128u, 2048u, p.halo_bo ? sx : 0u);
               const uint64_t bdesc = umma_smem_desc(smem_u32(sB + stage * b_bytes), 128);
 #pragma unroll
               for (int k = 0; k < 4; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ch | t | k) != 0 ? 1u : 0u);
@@ -217,7 +237,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint64_t adesc = umma_smem_desc(smem_u32(sA + stage * a_bytes), row_bytes);
-          const uint64_t bdesc = umma_smem_desc(smem_u32(sB + stage * b_bytes), row_bytes);
+          const uint64_t bdesc = umma_smem_desc(smem_u32(sB + (p.b_res ? kb : stage) * b_bytes), row_bytes);
           for (int k = 0; k < kpb; ++k) {
             // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in the (addr>>4) field
             umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
@@ -234,9 +254,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     // ===================== epilogue: 8 warps; warps q and q+4 share TMEM lane quarter q and split the
     // 16-column chunks between them (even / odd); thread == output row in the register phase ============
     const int ew = warp & 3;                   // TMEM lane quarter this warp may access
-    const int half = (warp - 4) >> 2;          // which chunks of a pass this warp converts
+    const int half = (warp - 4) >> 2;          // which 16-column chunks of a pass this warp converts (mod kColGroups)
     const int row = ew * 32 + lane;            // row of the 128-pixel tile
-    const int et = threadIdx.x - 128;          // 0..255
+    const int et = threadIdx.x - 128;          // 0..kEpiThreads-1
     const int TWm = (1 << p.lTW) - 1, THm = (1 << p.lTH) - 1;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -269,7 +289,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           }
         }
         named_bar_sync(1, kEpiThreads);                          // staging buffer free
-        for (int c = half * 16; c < chn; c += 32) {
+        for (int c = half * 16; c < chn; c += 16 * kColGroups) {
           uint32_t v[16];
           tmem_ld16(t_row + cc0 + c, v);
           const int gcol = nb * p.BN + cc0 + c;  // global output channel of v[0]
@@ -576,7 +596,23 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
   const int stage_bytes = kTileM * p.BK * 2 + BN * p.BK * 2;
   const int fixed = 1024 /*align slack*/ + staging + d.Cout * 4 /*bias*/ + 256 /*barriers*/;
   int S;
-  if (p.halo) {
+  static const int bres_env = getenv("CC_BRES") ? atoi(getenv("CC_BRES")) : 1;
+  const int bres_bytes = BN * p.BK * 2 * p.num_taps * p.chunks_per_tap;
+  p.b_res = (bres_env && p.n_blocks == 1 && bres_bytes <= 80 * 1024) ? 1 : 0;
+  if (p.b_res) {   // must leave room for 2 halo stages / >= 4 A stages, else stream the weights as usual
+    if (p.halo ? (fixed + 2 * p.halo_bytes + bres_bytes > kMaxSmem)
+               : ((kMaxSmem - fixed - bres_bytes) / (kTileM * p.BK * 2) < 4))
+      p.b_res = 0;
+  }
+  if (p.b_res && p.halo) {
+    S = 2;  // B ring unused
+    L->smem_bytes = fixed + 2 * p.halo_bytes + bres_bytes;
+  } else if (p.b_res) {
+    const int a_bytes = kTileM * p.BK * 2;
+    S = (kMaxSmem - fixed - bres_bytes) / a_bytes;
+    if (S > 8) S = 8;
+    L->smem_bytes = fixed + bres_bytes + S * a_bytes;
+  } else if (p.halo) {
     const int b_bytes = BN * 128;
     S = (kMaxSmem - fixed - 2 * p.halo_bytes) / b_bytes;
     if (S > 8) S = 8;
@@ -588,8 +624,6 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
   } else {
     S = (kMaxSmem - fixed) / stage_bytes;
     if (S > 8) S = 8;
-    const int num_kb = p.num_taps * p.chunks_per_tap;
-    if (S > num_kb + 1 && num_kb >= 2) S = num_kb + 1;  // no point in more stages than k-blocks (+1 for the next tile)
     CC_REQUIRE(S >= 2, "conv_gemm: tile does not fit shared memory (BN=%d BK=%d)", BN, p.BK);
     L->smem_bytes = fixed + S * stage_bytes;
   }
