@@ -152,6 +152,15 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t 
 }
 // Same, for a 128B-swizzled K-major view whose 8-row groups are `sbo_bytes` apart and whose start may be shifted by
 // whole 128-B rows inside the swizzle atom (halo views): base_offset carries (start >> 7) & 7 when requested.
+__device__ __forceinline__ uint64_t umma_smem_desc_halo(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t row_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= (row_bytes == 128 ? 2ull : 4ull) << 61;   // SWIZZLE_128B / SWIZZLE_64B (the XOR is on absolute smem address bits)
+  return d;
+}
 __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t base_offset) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);

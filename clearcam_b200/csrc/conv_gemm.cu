@@ -30,19 +30,32 @@ static constexpr int kTileM = 128;
 static constexpr uint32_t kTmemCols = 512;
 static constexpr int kMaxSmem = 232448;  // 227 KB
 
+__device__ __forceinline__ float tanh_approx(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x));
+  return t;
+}
+
+// Epilogue activations.  The SFU (MUFU) pipe issues 16 ops/clk/SM, so an activation that needs two of them
+// (ex2 + rcp) costs 2 x 128 x BN / 16 cycles per tile — more than the MMA time of every small-K layer.
+//   ACT_SILU       : x*sigmoid(x) = h + h*tanh(h), h = x/2 : ONE MUFU (tanh.approx.f32, |abs err| <= 2^-11 on tanh, i.e.
+//                    <= |x| * 2.4e-4 on the result, below the bf16 rounding of the stored value for x > -2)
+//   ACT_SILU_EXACT : x / (1 + 2^(-x log2 e)) with ex2.approx + rcp.approx (two MUFU, ~1e-7 relative)
+//   ACT_GELU_TANH  : 0.5x(1+tanh(sqrt(2/pi)(x+0.044715x^3)))  (models/objects.py:125 gelu()), one MUFU
 template <int ACT>
 __device__ __forceinline__ float act_apply(float x) {
   if (ACT == ACT_SILU) {
-    // x * 1/(1 + 2^(-x*log2e)) with the two raw MUFU approximations (no range fix-up branches)
+    const float h = 0.5f * x;
+    return fmaf(h, tanh_approx(h), h);
+  } else if (ACT == ACT_SILU_EXACT) {
     float e, r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
     return x * r;
   } else if (ACT == ACT_GELU_TANH) {
-    // 0.5x(1+tanh(sqrt(2/pi)(x+0.044715x^3))), tanh(u) = 1 - 2/(1+exp(2u))   (models/objects.py:125 gelu())
-    const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
-    const float t = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * u));
-    return 0.5f * x * (1.0f + t);
+    const float u = 0.7978845608028654f * fmaf(0.044715f * x * x, x, x);
+    const float h = 0.5f * x;
+    return fmaf(h, tanh_approx(u), h);
   }
   return x;
 }
@@ -137,7 +150,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       if (p.halo) {
         int sa = 0;
         uint32_t pa = 0;
-        const int cin = p.chunks_per_tap * 64;
+        const int cin = p.chunks_per_tap * p.BK;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
           const int nb = tile % p.n_blocks;
           const int m = tile / p.n_blocks;
@@ -147,13 +160,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           for (int ch = 0; ch < p.chunks_per_tap; ++ch) {
             mbar_wait(&aempty_bar[sa], pa ^ 1);
             mbar_arrive_expect_tx(&afull_bar[sa], p.halo_bytes);
-            tma_load_5d(sA + sa * p.halo_bytes, &p.tmA, &afull_bar[sa], ch * 64, w0 - 1, n0, h0 - 1, 0);
+            tma_load_5d(sA + sa * p.halo_bytes, &p.tmA, &afull_bar[sa], ch * p.BK, w0 - 1, n0, h0 - 1, 0);
             if (++sa == 2) { sa = 0; pa ^= 1; }
             if (!p.b_res)
             for (int t = 0; t < 9; ++t) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
               mbar_arrive_expect_tx(&full_bar[stage], b_bytes);
-              tma_load_2d(sB + stage * b_bytes, &p.tmB, &full_bar[stage], t * cin + ch * 64, nb * p.BN);
+              tma_load_2d(sB + stage * b_bytes, &p.tmB, &full_bar[stage], t * cin + ch * p.BK, nb * p.BN);
               if (++stage == S) { stage = 0; phase ^= 1; }
             }
           }
@@ -206,18 +219,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             const uint32_t a_base = smem_u32(sA + sa * p.halo_bytes);
             for (int t = 0; t < 9; ++t) {
               const uint32_t r = t / 3, sx = t - 3 * r;
-              const uint64_t adesc = umma_smem_desc_sw128(a_base + (r * tn16 + sx) * 128u, 2048u, p.halo_bo ? sx : 0u);
+              // halo rows are 16 px x row_bytes apart per 8-row group; the tap view starts (r, sx) pixels into the halo
+              const uint64_t adesc = umma_smem_desc_halo(a_base + (r * tn16 + sx) * row_bytes, 16u * row_bytes, row_bytes);
               if (p.b_res) {
-                const uint64_t bdesc = umma_smem_desc(smem_u32(sB + (t * p.chunks_per_tap + ch) * b_bytes), 128);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ch | t | k) != 0 ? 1u : 0u);
+                const uint64_t bdesc = umma_smem_desc(smem_u32(sB + (t * p.chunks_per_tap + ch) * b_bytes), row_bytes);
+                for (int k = 0; k < kpb; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ch | t | k) != 0 ? 1u : 0u);
                 continue;
               }
               mbar_wait(&full_bar[stage], phase);
               tc_fence_after();
-              const uint64_t bdesc = umma_smem_desc(smem_u32(sB + stage * b_bytes), 128);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ch | t | k) != 0 ? 1u : 0u);
+              const uint64_t bdesc = umma_smem_desc(smem_u32(sB + stage * b_bytes), row_bytes);
+              for (int k = 0; k < kpb; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ch | t | k) != 0 ? 1u : 0u);
               umma_commit(&empty_bar[stage]);
               if (++stage == S) { stage = 0; phase ^= 1; }
             }
@@ -478,7 +490,7 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
   // halo mainloop for 3x3 stride-1 convs with 64-channel chunks: tile = 8 px wide x (TH rows x TN images), TH*TN = 16
   static const int halo_env = getenv("CC_HALO") ? atoi(getenv("CC_HALO")) : 1;
   static const int halo_bo_env = getenv("CC_HALO_BO") ? atoi(getenv("CC_HALO_BO")) : 0;
-  p.halo = (halo_env && d.k == 3 && d.stride == 1 && d.Cin % 64 == 0) ? 1 : 0;
+  p.halo = (halo_env && d.k == 3 && d.stride == 1 && d.Cin % 32 == 0) ? 1 : 0;   // BK = 64 (128-B rows) or 32 (64-B rows)
   p.halo_bo = halo_bo_env;
   if (p.halo) {
     double be = -1;
@@ -489,7 +501,7 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
       if (eff > be) { be = eff; p.lTH = lh; p.lTN = 4 - lh; }
     }
     p.lTW = 3;
-    p.halo_bytes = 64 * 16 * (1 << p.lTN) * ((1 << p.lTH) + 2) * 2;
+    p.halo_bytes = p.BK * 16 * (1 << p.lTN) * ((1 << p.lTH) + 2) * 2;
   }
   const int TW = 1 << p.lTW, TH = 1 << p.lTH, TN = 1 << p.lTN;
   p.tiles_w = (Wout + TW - 1) / TW;
@@ -527,7 +539,7 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
       // (C, W, N, H): the box [64 ch][16 px][TN images][TH+2 rows] lands in smem as [row][image][pixel][128 B]
       dims[0] = d.Cin; dims[1] = d.Win; dims[2] = d.N; dims[3] = d.Hin; dims[4] = 1;
       strides[0] = px; strides[1] = px * d.Win * d.Hin; strides[2] = px * d.Win; strides[3] = px * d.Win * d.Hin * d.N;
-      box[0] = 64; box[1] = 16; box[2] = TN; box[3] = TH + 2; box[4] = 1;
+      box[0] = p.BK; box[1] = 16; box[2] = TN; box[3] = TH + 2; box[4] = 1;
     } else if (!p.s2) {
       dims[0] = d.Cin; dims[1] = d.Win; dims[2] = d.Hin; dims[3] = d.N; dims[4] = 1;
       strides[0] = px; strides[1] = px * d.Win; strides[2] = px * d.Win * d.Hin; strides[3] = px * d.Win * d.Hin * d.N;
@@ -569,7 +581,7 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
   if (p.tma_store) {
     // double-buffer the staging when the pipeline still gets >= 4 stages (per-tap mode) / 3 B stages (halo mode)
     const int one = kTileM * CH * es;
-    const int stage_b = p.halo ? BN * 128 : kTileM * p.BK * 2 + BN * p.BK * 2;
+    const int stage_b = p.halo ? BN * p.BK * 2 : kTileM * p.BK * 2 + BN * p.BK * 2;
     const int other = 1024 + d.Cout * 4 + 256 + (p.halo ? 2 * p.halo_bytes : 0);
     if ((kMaxSmem - other - 2 * one) / stage_b >= (p.halo ? 3 : 4)) p.stg_bufs = 2;
     void* base = reinterpret_cast<uint8_t*>(d.out) + size_t(d.out_co) * es;
@@ -613,7 +625,7 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
     if (S > 8) S = 8;
     L->smem_bytes = fixed + bres_bytes + S * a_bytes;
   } else if (p.halo) {
-    const int b_bytes = BN * 128;
+    const int b_bytes = BN * p.BK * 2;
     S = (kMaxSmem - fixed - 2 * p.halo_bytes) / b_bytes;
     if (S > 8) S = 8;
     if (S < 3) {   // does not fit: fall back to the per-tap mainloop
@@ -658,11 +670,16 @@ static int launch_variant(const GemmLaunch& L, cudaStream_t stream) {
 
 int conv_gemm_launch(const GemmLaunch& L, cudaStream_t stream) {
   const bool f32 = L.p.out_f32 != 0;
-  switch (L.p.act) {
+  static const int exact_env = getenv("CC_SILU_EXACT") ? atoi(getenv("CC_SILU_EXACT")) : 0;
+  int act = L.p.act;
+  if (act == ACT_SILU && exact_env) act = ACT_SILU_EXACT;
+  switch (act) {
     case ACT_NONE: return f32 ? launch_variant<ACT_NONE, true>(L, stream) : launch_variant<ACT_NONE, false>(L, stream);
     case ACT_SILU: return f32 ? launch_variant<ACT_SILU, true>(L, stream) : launch_variant<ACT_SILU, false>(L, stream);
     case ACT_GELU_TANH:
       return f32 ? launch_variant<ACT_GELU_TANH, true>(L, stream) : launch_variant<ACT_GELU_TANH, false>(L, stream);
+    case ACT_SILU_EXACT:
+      return f32 ? launch_variant<ACT_SILU_EXACT, true>(L, stream) : launch_variant<ACT_SILU_EXACT, false>(L, stream);
   }
   set_error("conv_gemm: unknown activation %d", L.p.act);
   return CC_ERR_INVALID;
