@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   const uint32_t pitch = p.tma_store ? CH * es : CH * es + 16;
   const uint32_t stg_bytes = (kTileM * pitch + 15) & ~15u;           // one staging buffer
 
-  const uint32_t a_region = p.halo ? 2u * p.halo_bytes : S * a_bytes;   // halo mode: 2 halo stages, S = B stages
+  const uint32_t a_region = p.halo ? p.halo_stages * p.halo_bytes : S * a_bytes;   // halo mode: S = B stages
   uint8_t* sA = smem;
   uint8_t* sB = sA + a_region;
   const int num_kb_all = p.num_taps * p.chunks_per_tap;
@@ -95,10 +95,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   uint64_t* empty_bar = bars + S;
   uint64_t* tfull_bar = bars + 2 * S;
   uint64_t* tempty_bar = bars + 2 * S + 2;
-  uint64_t* afull_bar = bars + 2 * S + 4;     // halo mode
-  uint64_t* aempty_bar = bars + 2 * S + 6;
-  uint64_t* bres_bar = bars + 2 * S + 8;      // resident-B mode
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 9);
+  uint64_t* afull_bar = bars + 2 * S + 4;     // halo mode (up to 4 stages)
+  uint64_t* aempty_bar = bars + 2 * S + 8;
+  uint64_t* bres_bar = bars + 2 * S + 12;     // resident-B mode
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 13);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
@@ -113,6 +113,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], kEpiThreads);
+    }
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&afull_bar[i], 1);
       mbar_init(&aempty_bar[i], 1);
     }
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             mbar_wait(&aempty_bar[sa], pa ^ 1);
             mbar_arrive_expect_tx(&afull_bar[sa], p.halo_bytes);
             tma_load_5d(sA + sa * p.halo_bytes, &p.tmA, &afull_bar[sa], ch * p.BK, w0 - 1, n0, h0 - 1, 0);
-            if (++sa == 2) { sa = 0; pa ^= 1; }
+            if (++sa == p.halo_stages) { sa = 0; pa ^= 1; }
             if (!p.b_res)
             for (int t = 0; t < 9; ++t) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -234,7 +236,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
               if (++stage == S) { stage = 0; phase ^= 1; }
             }
             umma_commit(&aempty_bar[sa]);
-            if (++sa == 2) { sa = 0; pa ^= 1; }
+            if (++sa == p.halo_stages) { sa = 0; pa ^= 1; }
           }
           umma_commit(&tfull_bar[acc]);
           acc ^= 1;
@@ -582,8 +584,9 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
     // double-buffer the staging when the pipeline still gets >= 4 stages (per-tap mode) / 3 B stages (halo mode)
     const int one = kTileM * CH * es;
     const int stage_b = p.halo ? BN * p.BK * 2 : kTileM * p.BK * 2 + BN * p.BK * 2;
-    const int other = 1024 + d.Cout * 4 + 256 + (p.halo ? 2 * p.halo_bytes : 0);
-    if ((kMaxSmem - other - 2 * one) / stage_b >= (p.halo ? 3 : 4)) p.stg_bufs = 2;
+    const int other = 1024 + d.Cout * 4 + 256;
+    if (!p.halo && (kMaxSmem - other - 2 * one) / stage_b >= 4) p.stg_bufs = 2;
+    if (p.halo && kMaxSmem - other - 2 * one - 3 * stage_b >= 3 * p.halo_bytes) p.stg_bufs = 2;
     void* base = reinterpret_cast<uint8_t*>(d.out) + size_t(d.out_co) * es;
     cuuint64_t dims[5], strides[4];
     cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
@@ -609,31 +612,39 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
   const int fixed = 1024 /*align slack*/ + staging + d.Cout * 4 /*bias*/ + 256 /*barriers*/;
   int S;
   static const int bres_env = getenv("CC_BRES") ? atoi(getenv("CC_BRES")) : 1;
+  static const int hst_env = getenv("CC_HALO_STAGES") ? atoi(getenv("CC_HALO_STAGES")) : 0;
   const int bres_bytes = BN * p.BK * 2 * p.num_taps * p.chunks_per_tap;
   p.b_res = (bres_env && p.n_blocks == 1 && bres_bytes <= 80 * 1024) ? 1 : 0;
-  if (p.b_res) {   // must leave room for 2 halo stages / >= 4 A stages, else stream the weights as usual
-    if (p.halo ? (fixed + 2 * p.halo_bytes + bres_bytes > kMaxSmem)
-               : ((kMaxSmem - fixed - bres_bytes) / (kTileM * p.BK * 2) < 4))
-      p.b_res = 0;
-  }
-  if (p.b_res && p.halo) {
-    S = 2;  // B ring unused
-    L->smem_bytes = fixed + 2 * p.halo_bytes + bres_bytes;
-  } else if (p.b_res) {
+  p.halo_stages = 2;
+  if (p.halo) {
+    const int b_bytes = BN * p.BK * 2;
+    // budget: staging (already in `fixed`), then weights (resident, or a ring of >= 3 taps), then as many halo
+    // buffers as fit (2..4): a halo chunk is only 9 taps of MMA work, so 2 buffers cannot hide the TMA latency
+    int avail = kMaxSmem - fixed;
+    if (p.b_res && avail - bres_bytes < 2 * p.halo_bytes) p.b_res = 0;
+    int wbytes;
+    if (p.b_res) { wbytes = bres_bytes; S = 2; }
+    else {
+      S = 3;
+      while (S < 6 && avail - (S + 1) * b_bytes >= 3 * p.halo_bytes) ++S;   // extra weight stages only once 3 halo buffers fit
+      wbytes = S * b_bytes;
+    }
+    int hs = (avail - wbytes) / p.halo_bytes;
+    if (hs > 4) hs = 4;
+    if (hst_env >= 2 && hst_env <= 4 && hst_env < hs) hs = hst_env;
+    if (hs < 2) {   // does not fit: caller falls back
+      set_error("conv_gemm: halo tile does not fit (BN=%d halo=%d B)", BN, p.halo_bytes);
+      return CC_ERR_INVALID;
+    }
+    p.halo_stages = hs;
+    L->smem_bytes = fixed + wbytes + hs * p.halo_bytes;
+  } else if (p.b_res && (kMaxSmem - fixed - bres_bytes) / (kTileM * p.BK * 2) >= 4) {
     const int a_bytes = kTileM * p.BK * 2;
     S = (kMaxSmem - fixed - bres_bytes) / a_bytes;
     if (S > 8) S = 8;
     L->smem_bytes = fixed + bres_bytes + S * a_bytes;
-  } else if (p.halo) {
-    const int b_bytes = BN * p.BK * 2;
-    S = (kMaxSmem - fixed - 2 * p.halo_bytes) / b_bytes;
-    if (S > 8) S = 8;
-    if (S < 3) {   // does not fit: fall back to the per-tap mainloop
-      set_error("conv_gemm: halo tile does not fit (BN=%d halo=%d B)", BN, p.halo_bytes);
-      return CC_ERR_INVALID;
-    }
-    L->smem_bytes = fixed + 2 * p.halo_bytes + S * b_bytes;
   } else {
+    p.b_res = 0;
     S = (kMaxSmem - fixed) / stage_bytes;
     if (S > 8) S = 8;
     CC_REQUIRE(S >= 2, "conv_gemm: tile does not fit shared memory (BN=%d BK=%d)", BN, p.BK);

@@ -43,6 +43,7 @@ struct GemmParams {
   // halo mainloop (3x3 stride-1, Cin % 64 == 0): one TMA load of the (TH+2) x 16-pixel halo per 64-channel chunk,
   // the nine taps are shifted shared-memory descriptor views of it
   int32_t halo, halo_bytes, halo_bo;  // enabled / bytes per halo stage / descriptor base_offset mode
+  int32_t halo_stages;                // 2..4 halo buffers in flight
   int32_t tma_store, stg_bufs;        // epilogue stores through TMA from 128B-swizzled staging (1 or 2 buffers)
   int32_t b_res;                      // weights of the (single) N block stay resident in smem for the whole kernel
 };

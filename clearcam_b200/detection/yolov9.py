@@ -191,6 +191,54 @@ class YOLOv9:
                                     ptr(rawt), stream_ptr(stream)), "cc_yolo_forward")
         return (out, rawt) if raw else out
 
+    def detect_pipelined(self, host_batches, depth: int = 2):
+        """Throughput API for host-resident frames: iterates over pinned host batches [B,H,W,3] and yields one
+        pinned host result (B,300,6) per batch.  The H2D copy of batch i+1 and the D2H read of result i-1 run on a side
+        stream while batch i computes (double-buffered device frames / results), so PCIe time hides behind the kernels."""
+        main = torch.cuda.current_stream()
+        side = getattr(self, "_side_stream", None)
+        if side is None:
+            side = self._side_stream = torch.cuda.Stream()
+        it = iter(host_batches)
+        slots = []          # per in-flight batch: (device frames, device out, host out, ready event, done event)
+        pending = []
+
+        def stage(hb):
+            if not hb.is_pinned():
+                hb = hb.pin_memory()
+            with torch.cuda.stream(side):
+                dev = hb.to("cuda", non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            return dev, ev
+
+        nxt = next(it, None)
+        staged = stage(nxt) if nxt is not None else None
+        while staged is not None:
+            dev, ev = staged
+            nxt = next(it, None)
+            staged = stage(nxt) if nxt is not None else None          # H2D of the next batch overlaps this compute
+            main.wait_event(ev)
+            out = self.detect_batch(dev)
+            done = torch.cuda.Event()
+            done.record(main)
+            dev.record_stream(main)
+            with torch.cuda.stream(side):
+                side.wait_event(done)
+                host_out = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+                host_out.copy_(out, non_blocking=True)
+                fin = torch.cuda.Event()
+                fin.record(side)
+            out.record_stream(side)
+            pending.append((host_out, fin))
+            while len(pending) > depth:
+                h, f = pending.pop(0)
+                f.synchronize()
+                yield h
+        for h, f in pending:
+            f.synchronize()
+            yield h
+
     def __call__(self, frame):
         """frame: HWC BGR image (uint8 or float32; numpy / torch / anything with .numpy()).  -> (300,6)"""
         t = self._as_device_frames(frame)

@@ -9,6 +9,9 @@ shapes = [  # N,H,W,Cin,Cout,k,s
     (32, 40, 40, 256, 256, 3, 1),
     (32, 160, 160, 64, 64, 3, 1),
     (32, 80, 80, 256, 320, 3, 1),
+    (32, 80, 80, 128, 128, 3, 1),
+    (32, 160, 160, 256, 256, 1, 1),
+    (32, 160, 160, 32, 32, 3, 1),
 ]
 sel = [int(a) for a in sys.argv[2:]] or range(len(shapes))
 for si in sel:
