@@ -198,51 +198,68 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      const uint32_t idesc = umma_idesc_f16(kTileM, p.BN, p.ab_fmt);
-      const int kpb = p.BK / 16;  // UMMA_K = 16 for 16-bit inputs
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      if (p.b_res) { mbar_wait(bres_bar, 0); tc_fence_after(); }
-      if (p.halo) {
-        int sa = 0;
-        uint32_t pa = 0;
-        const uint32_t tn16 = 16u << p.lTN;  // halo pixels per halo row block (TN images x 16 px)
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-          mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+    // ===================== MMA issuer =====================
+    // The WHOLE warp runs this loop with warp-uniform values and one elected lane issues: descriptors and TMEM
+    // addresses then live in uniform registers (a single active lane made ptxas emit an ELECT/R2UR.BROADCAST loop per
+    // tcgen05.mma — ~100 SASS instructions per k-block, more than the 256 tensor cycles of a 128x128x64 block).
+    const uint32_t idesc = umma_idesc_f16(kTileM, p.BN, p.ab_fmt);
+    const int kpb = p.BK / 16;  // UMMA_K = 16 for 16-bit inputs
+    // constant upper parts of the K-major swizzled descriptors (LBO=1, SBO, version 1, swizzle mode)
+    const uint64_t lay = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);
+    const uint64_t dconst = (1ull << 16) | (1ull << 46) | (lay << 61);
+    const uint64_t d_tile = dconst | (static_cast<uint64_t>((8u * row_bytes) >> 4) << 32);    // dense 128-row tiles
+    const uint64_t d_halo = dconst | (static_cast<uint64_t>((16u * row_bytes) >> 4) << 32);   // halo views: 16-px row pitch
+    const uint32_t sA16 = (smem_u32(sA) & 0x3FFFF) >> 4, sB16 = (smem_u32(sB) & 0x3FFFF) >> 4;
+    const uint32_t a16 = a_bytes >> 4, b16 = b_bytes >> 4, h16 = p.halo_bytes >> 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    if (p.b_res) { mbar_wait(bres_bar, 0); tc_fence_after(); }
+    if (p.halo) {
+      int sa = 0;
+      uint32_t pa = 0;
+      const uint32_t rstep16 = ((16u << p.lTN) * row_bytes) >> 4;  // one halo row block (TN images x 16 px), in 16-B units
+      const uint32_t sstep16 = row_bytes >> 4;                      // one pixel
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        bool first = true;
+        for (int ch = 0; ch < p.chunks_per_tap; ++ch) {
+          mbar_wait(&afull_bar[sa], pa);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * 256;
-          for (int ch = 0; ch < p.chunks_per_tap; ++ch) {
-            mbar_wait(&afull_bar[sa], pa);
-            tc_fence_after();
-            const uint32_t a_base = smem_u32(sA + sa * p.halo_bytes);
-            for (int t = 0; t < 9; ++t) {
-              const uint32_t r = t / 3, sx = t - 3 * r;
-              // halo rows are 16 px x row_bytes apart per 8-row group; the tap view starts (r, sx) pixels into the halo
-              const uint64_t adesc = umma_smem_desc_halo(a_base + (r * tn16 + sx) * row_bytes, 16u * row_bytes, row_bytes);
+          const uint64_t a_base = d_halo | (sA16 + sa * h16);
+          for (int r = 0; r < 3; ++r)
+            for (int sx = 0; sx < 3; ++sx) {
+              const uint64_t adesc = a_base + (r * rstep16 + sx * sstep16);
+              uint64_t bdesc;
               if (p.b_res) {
-                const uint64_t bdesc = umma_smem_desc(smem_u32(sB + (t * p.chunks_per_tap + ch) * b_bytes), row_bytes);
-                for (int k = 0; k < kpb; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ch | t | k) != 0 ? 1u : 0u);
-                continue;
+                bdesc = d_tile | (sB16 + ((r * 3 + sx) * p.chunks_per_tap + ch) * b16);
+              } else {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                bdesc = d_tile | (sB16 + stage * b16);
               }
-              mbar_wait(&full_bar[stage], phase);
-              tc_fence_after();
-              const uint64_t bdesc = umma_smem_desc(smem_u32(sB + stage * b_bytes), row_bytes);
-              for (int k = 0; k < kpb; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ch | t | k) != 0 ? 1u : 0u);
-              umma_commit(&empty_bar[stage]);
-              if (++stage == S) { stage = 0; phase ^= 1; }
+              if (elect_one()) {
+                if (first) umma_f16_c<false>(d_tmem, adesc, bdesc, idesc); else umma_f16_c<true>(d_tmem, adesc, bdesc, idesc);
+                for (int k = 1; k < kpb; ++k) umma_f16_c<true>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc);
+                if (!p.b_res) umma_commit(&empty_bar[stage]);
+              }
+              __syncwarp();
+              first = false;
+              if (!p.b_res) { if (++stage == S) { stage = 0; phase ^= 1; } }
             }
-            umma_commit(&aempty_bar[sa]);
-            if (++sa == p.halo_stages) { sa = 0; pa ^= 1; }
-          }
-          umma_commit(&tfull_bar[acc]);
-          acc ^= 1;
-          if (acc == 0) acc_phase ^= 1;
+          if (elect_one()) umma_commit(&aempty_bar[sa]);
+          __syncwarp();
+          if (++sa == p.halo_stages) { sa = 0; pa ^= 1; }
         }
-      } else
+        if (elect_one()) umma_commit(&tfull_bar[acc]);
+        __syncwarp();
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    } else {
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -250,16 +267,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t adesc = umma_smem_desc(smem_u32(sA + stage * a_bytes), row_bytes);
-          const uint64_t bdesc = umma_smem_desc(smem_u32(sB + (p.b_res ? kb : stage) * b_bytes), row_bytes);
-          for (int k = 0; k < kpb; ++k) {
-            // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in the (addr>>4) field
-            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          const uint64_t adesc = d_tile | (sA16 + stage * a16);
+          const uint64_t bdesc = d_tile | (sB16 + (p.b_res ? kb : stage) * b16);
+          if (elect_one()) {
+            if (kb == 0) umma_f16_c<false>(d_tmem, adesc, bdesc, idesc); else umma_f16_c<true>(d_tmem, adesc, bdesc, idesc);
+            for (int k = 1; k < kpb; ++k) umma_f16_c<true>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc);
+            umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs have read it
           }
-          umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs have read it
+          __syncwarp();
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        if (elect_one()) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
