@@ -65,6 +65,99 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// ---- MMA issuer role (warp 1), templated on the number of UMMA_K=16 steps per k-block so the issue sequence is
+// straight-line code.  The WHOLE warp runs the loop with warp-uniform values and one elected lane issues: descriptors
+// and TMEM addresses then live in uniform registers (a single active lane made ptxas wrap every tcgen05.mma in an
+// ELECT/R2UR.BROADCAST loop: ~100 SASS instructions per k-block, more than its 256 tensor cycles at BN=128).
+template <int KPB>
+__device__ __forceinline__ void mma_issuer(const GemmParams& p, uint8_t* sA, uint8_t* sB, uint32_t row_bytes, uint32_t a_bytes,
+                                           uint32_t b_bytes, int S, int num_kb, uint64_t* full_bar, uint64_t* empty_bar,
+                                           uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* afull_bar,
+                                           uint64_t* aempty_bar, uint64_t* bres_bar, uint32_t tmem_base) {
+    const uint32_t idesc = umma_idesc_f16(kTileM, p.BN, p.ab_fmt);
+    // constant upper parts of the K-major swizzled descriptors (LBO=1, SBO, version 1, swizzle mode)
+    const uint64_t lay = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);
+    const uint64_t dconst = (1ull << 16) | (1ull << 46) | (lay << 61);
+    const uint64_t d_tile = dconst | (static_cast<uint64_t>((8u * row_bytes) >> 4) << 32);    // dense 128-row tiles
+    const uint64_t d_halo = dconst | (static_cast<uint64_t>((16u * row_bytes) >> 4) << 32);   // halo views: 16-px row pitch
+    const uint32_t sA16 = (smem_u32(sA) & 0x3FFFF) >> 4, sB16 = (smem_u32(sB) & 0x3FFFF) >> 4;
+    const uint32_t a16 = a_bytes >> 4, b16 = b_bytes >> 4, h16 = p.halo_bytes >> 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    if (p.b_res) { mbar_wait(bres_bar, 0); tc_fence_after(); }
+    if (p.halo) {
+      int sa = 0;
+      uint32_t pa = 0;
+      const uint32_t rstep16 = ((16u << p.lTN) * row_bytes) >> 4;  // one halo row block (TN images x 16 px), in 16-B units
+      const uint32_t sstep16 = row_bytes >> 4;                      // one pixel
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        bool first = true;
+        for (int ch = 0; ch < p.chunks_per_tap; ++ch) {
+          mbar_wait(&afull_bar[sa], pa);
+          tc_fence_after();
+          const uint64_t a_base = d_halo | (sA16 + sa * h16);
+          for (int r = 0; r < 3; ++r)
+            for (int sx = 0; sx < 3; ++sx) {
+              const uint64_t adesc = a_base + (r * rstep16 + sx * sstep16);
+              uint64_t bdesc;
+              if (p.b_res) {
+                bdesc = d_tile | (sB16 + ((r * 3 + sx) * p.chunks_per_tap + ch) * b16);
+              } else {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                bdesc = d_tile | (sB16 + stage * b16);
+              }
+              if (elect_one()) {
+                if (first) umma_f16_c<false>(d_tmem, adesc, bdesc, idesc); else umma_f16_c<true>(d_tmem, adesc, bdesc, idesc);
+                #pragma unroll
+                for (int k = 1; k < KPB; ++k) umma_f16_c<true>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc);
+                if (!p.b_res) umma_commit(&empty_bar[stage]);
+              }
+              __syncwarp();
+              first = false;
+              if (!p.b_res) { if (++stage == S) { stage = 0; phase ^= 1; } }
+            }
+          if (elect_one()) umma_commit(&aempty_bar[sa]);
+          __syncwarp();
+          if (++sa == p.halo_stages) { sa = 0; pa ^= 1; }
+        }
+        if (elect_one()) umma_commit(&tfull_bar[acc]);
+        __syncwarp();
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    } else {
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = d_tile | (sA16 + stage * a16);
+          const uint64_t bdesc = d_tile | (sB16 + (p.b_res ? kb : stage) * b16);
+          if (elect_one()) {
+            if (kb == 0) umma_f16_c<false>(d_tmem, adesc, bdesc, idesc); else umma_f16_c<true>(d_tmem, adesc, bdesc, idesc);
+            #pragma unroll
+                for (int k = 1; k < KPB; ++k) umma_f16_c<true>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc);
+            umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs have read it
+          }
+          __syncwarp();
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+        if (elect_one()) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        __syncwarp();
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+}
+
 template <int ACT, bool F32>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -199,90 +292,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    // The WHOLE warp runs this loop with warp-uniform values and one elected lane issues: descriptors and TMEM
-    // addresses then live in uniform registers (a single active lane made ptxas emit an ELECT/R2UR.BROADCAST loop per
-    // tcgen05.mma — ~100 SASS instructions per k-block, more than the 256 tensor cycles of a 128x128x64 block).
-    const uint32_t idesc = umma_idesc_f16(kTileM, p.BN, p.ab_fmt);
-    const int kpb = p.BK / 16;  // UMMA_K = 16 for 16-bit inputs
-    // constant upper parts of the K-major swizzled descriptors (LBO=1, SBO, version 1, swizzle mode)
-    const uint64_t lay = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);
-    const uint64_t dconst = (1ull << 16) | (1ull << 46) | (lay << 61);
-    const uint64_t d_tile = dconst | (static_cast<uint64_t>((8u * row_bytes) >> 4) << 32);    // dense 128-row tiles
-    const uint64_t d_halo = dconst | (static_cast<uint64_t>((16u * row_bytes) >> 4) << 32);   // halo views: 16-px row pitch
-    const uint32_t sA16 = (smem_u32(sA) & 0x3FFFF) >> 4, sB16 = (smem_u32(sB) & 0x3FFFF) >> 4;
-    const uint32_t a16 = a_bytes >> 4, b16 = b_bytes >> 4, h16 = p.halo_bytes >> 4;
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    if (p.b_res) { mbar_wait(bres_bar, 0); tc_fence_after(); }
-    if (p.halo) {
-      int sa = 0;
-      uint32_t pa = 0;
-      const uint32_t rstep16 = ((16u << p.lTN) * row_bytes) >> 4;  // one halo row block (TN images x 16 px), in 16-B units
-      const uint32_t sstep16 = row_bytes >> 4;                      // one pixel
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * 256;
-        bool first = true;
-        for (int ch = 0; ch < p.chunks_per_tap; ++ch) {
-          mbar_wait(&afull_bar[sa], pa);
-          tc_fence_after();
-          const uint64_t a_base = d_halo | (sA16 + sa * h16);
-          for (int r = 0; r < 3; ++r)
-            for (int sx = 0; sx < 3; ++sx) {
-              const uint64_t adesc = a_base + (r * rstep16 + sx * sstep16);
-              uint64_t bdesc;
-              if (p.b_res) {
-                bdesc = d_tile | (sB16 + ((r * 3 + sx) * p.chunks_per_tap + ch) * b16);
-              } else {
-                mbar_wait(&full_bar[stage], phase);
-                tc_fence_after();
-                bdesc = d_tile | (sB16 + stage * b16);
-              }
-              if (elect_one()) {
-                if (first) umma_f16_c<false>(d_tmem, adesc, bdesc, idesc); else umma_f16_c<true>(d_tmem, adesc, bdesc, idesc);
-                for (int k = 1; k < kpb; ++k) umma_f16_c<true>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc);
-                if (!p.b_res) umma_commit(&empty_bar[stage]);
-              }
-              __syncwarp();
-              first = false;
-              if (!p.b_res) { if (++stage == S) { stage = 0; phase ^= 1; } }
-            }
-          if (elect_one()) umma_commit(&aempty_bar[sa]);
-          __syncwarp();
-          if (++sa == p.halo_stages) { sa = 0; pa ^= 1; }
-        }
-        if (elect_one()) umma_commit(&tfull_bar[acc]);
-        __syncwarp();
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
-      }
-    } else {
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * 256;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint64_t adesc = d_tile | (sA16 + stage * a16);
-          const uint64_t bdesc = d_tile | (sB16 + (p.b_res ? kb : stage) * b16);
-          if (elect_one()) {
-            if (kb == 0) umma_f16_c<false>(d_tmem, adesc, bdesc, idesc); else umma_f16_c<true>(d_tmem, adesc, bdesc, idesc);
-            for (int k = 1; k < kpb; ++k) umma_f16_c<true>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc);
-            umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs have read it
-          }
-          __syncwarp();
-          if (++stage == S) { stage = 0; phase ^= 1; }
-        }
-        if (elect_one()) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
-        __syncwarp();
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
-      }
-    }
+    if (p.BK == 64) mma_issuer<4>(p, sA, sB, row_bytes, a_bytes, b_bytes, S, num_kb, full_bar, empty_bar, tfull_bar, tempty_bar, afull_bar, aempty_bar, bres_bar, tmem_base);
+    else if (p.BK == 32) mma_issuer<2>(p, sA, sB, row_bytes, a_bytes, b_bytes, S, num_kb, full_bar, empty_bar, tfull_bar, tempty_bar, afull_bar, aempty_bar, bres_bar, tmem_base);
+    else mma_issuer<1>(p, sA, sB, row_bytes, a_bytes, b_bytes, S, num_kb, full_bar, empty_bar, tfull_bar, tempty_bar, afull_bar, aempty_bar, bres_bar, tmem_base);
   } else if (warp >= 4) {
     // ===================== epilogue: 8 warps; warps q and q+4 share TMEM lane quarter q and split the
     // 16-column chunks between them (even / odd); thread == output row in the register phase ============
