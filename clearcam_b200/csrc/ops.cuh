@@ -58,6 +58,10 @@ struct StemParams {
   TSlice out;                                  // [B,H/2,W/2,Cout]
 };
 int stem_launch(const StemParams& p, cudaStream_t s);
+// uint8 stem on tensor cores: im2col of the 3x3/s2 taps into a bf16 [B*Ho*Wo, 32] matrix (raw pixel values 0..255 are
+// exact in bf16; taps in (r,s,RGB) order = frame channel 2-c; columns 27..31 zero), consumed by conv_gemm with weights
+// bf16(w/255).
+int stem_im2col_launch(const uint8_t* frames, __nv_bfloat16* out, int B, int H, int W, cudaStream_t s);
 
 // Detect head tail: DFL softmax-expectation, dist2bbox, x stride, sigmoid, max/argmax, conf threshold
 // (detection/yolov9.py:209-219, 273-282, 263-271, 440-448).  Inputs are the fp32 logits of the three scales.

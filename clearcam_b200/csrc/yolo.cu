@@ -18,6 +18,7 @@
 #include "conv_gemm.cuh"
 #include "ops.cuh"
 #include <cmath>
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <string>
@@ -138,6 +139,7 @@ struct HostT { const float* p; long long n; };
 struct ConvW {           // device-resident, kernel layout
   __nv_bfloat16* w = nullptr;   // [Cout][k][k][Cin_eff]  (Cin_eff = Cin when dense, Cin/groups when grouped)
   float* wf32 = nullptr;        // stem only: fp32 [Cout][3][3][3]
+  __nv_bfloat16* wtc = nullptr; // stem only: bf16 [Cout][32] = w/255 in (r,s,c) order, zero padded (tensor-core uint8 path)
   float* bias = nullptr;
   int cin = 0, cout = 0, k = 0, groups = 1;   // groups == 1 -> dense (possibly block-diagonal expansion)
 };
@@ -147,7 +149,7 @@ static __nv_bfloat16 f2bf(float x) { return __float2bfloat16_rn(x); }
 struct T { __nv_bfloat16* p = nullptr; int cs = 0, co = 0, C = 0, H = 0, W = 0; bool image = false; };
 
 struct Op {
-  enum Kind { GEMM, DIRECT, AVGPAD, AVGMAX, MAXPOOL5, UPSAMPLE, CBFUSE, LETTERBOX, STEM, DECODE, POST } kind;
+  enum Kind { GEMM, DIRECT, AVGPAD, AVGMAX, MAXPOOL5, UPSAMPLE, CBFUSE, LETTERBOX, STEM, STEM_IM2COL, DECODE, POST } kind;
   GemmLaunch gemm;
   DirectConvParams direct;
   TSlice s_in, s_out;
@@ -229,7 +231,13 @@ struct YoloModel {
     ConvW cw;
     cw.cin = cin; cw.cout = cout_total; cw.k = k; cw.groups = dense ? 1 : groups;
     int rc;
-    if (stem) { if ((rc = upload(wf.data(), wf.size() * 4, reinterpret_cast<void**>(&cw.wf32)))) return rc; }
+    if (stem) {
+      if ((rc = upload(wf.data(), wf.size() * 4, reinterpret_cast<void**>(&cw.wf32)))) return rc;
+      std::vector<__nv_bfloat16> wt(static_cast<size_t>(cout_total) * 32, f2bf(0.f));
+      for (int co = 0; co < cout_total; ++co)
+        for (int kk = 0; kk < 27; ++kk) wt[static_cast<size_t>(co) * 32 + kk] = f2bf(wf[static_cast<size_t>(co) * 27 + kk] / 255.0f);
+      if ((rc = upload(wt.data(), wt.size() * 2, reinterpret_cast<void**>(&cw.wtc)))) return rc;
+    }
     else { if ((rc = upload(w.data(), w.size() * 2, reinterpret_cast<void**>(&cw.w)))) return rc; }
     if ((rc = upload(bias.data(), bias.size() * 4, reinterpret_cast<void**>(&cw.bias)))) return rc;
     convs[key] = cw;
@@ -418,8 +426,30 @@ int Builder::build() {
         if (in.image) {
           CC_REQUIRE(l.a == 3 && l.k == 3 && l.s == 2, "yolo: unexpected image conv");
           out = out_for(i, l.b, in.H / 2, in.W / 2);
-          Op op; op.kind = Op::STEM; op.name = pfx;
           const ConvW& cw = M.convs[pfx];
+          static const int stem_tc_env = getenv("CC_STEM_TC") ? atoi(getenv("CC_STEM_TC")) : 1;
+          if (!P.is_f32 && stem_tc_env && cw.cout % 16 == 0) {
+            // uint8 frames: raw pixel values are exact in bf16 -> im2col to [B*Ho*Wo, 32] and run the tensor-core GEMM
+            // with weights bf16(w/255)
+            const long long Mrows = static_cast<long long>(P.B) * (P.H / 2) * (P.W / 2);
+            __nv_bfloat16* cols = static_cast<__nv_bfloat16*>(dalloc(static_cast<size_t>(Mrows) * 32 * 2));
+            { Op op; op.kind = Op::STEM_IM2COL; op.name = pfx + ".im2col"; op.stem = StemParams{};
+              op.stem.in = net_in; op.stem.B = P.B; op.stem.H = P.H; op.stem.W = P.W;
+              op.s_out.p = cols; P.ops.push_back(std::move(op)); }
+            ConvDesc d{};
+            d.in = cols; d.in_cs = 32; d.in_co = 0; d.Cin = 32;
+            d.N = 1; d.Hin = 1; d.Win = static_cast<int>(Mrows); d.k = 1; d.stride = 1;
+            d.w = cw.wtc; d.bias = cw.bias;
+            d.out = out.p; d.out_cs = out.cs; d.out_co = out.co; d.Cout = cw.cout; d.out_f32 = 0; d.act = CC_ACT_SILU;
+            Op op; op.kind = Op::GEMM; op.name = pfx;
+            rc = conv_gemm_build(d, M.sms, &op.gemm);
+            if (rc) break;
+            op.gemm.flops = 2.0 * Mrows * cw.cout * 27;
+            P.conv_flops += op.gemm.flops;
+            P.ops.push_back(std::move(op));
+            break;
+          }
+          Op op; op.kind = Op::STEM; op.name = pfx;
           op.stem = StemParams{};
           op.stem.in = net_in; op.stem.is_f32 = P.is_f32; op.stem.B = P.B; op.stem.H = P.H; op.stem.W = P.W;
           op.stem.w = cw.wf32; op.stem.bias = cw.bias; op.stem.Cout = cw.cout; op.stem.out = ts(out);
@@ -585,6 +615,10 @@ static int plan_run(YoloPlan& P, const void* d_frames, float* d_out, float* d_ra
       case Op::CBFUSE: rc = cbfuse_launch(op.cbf, st); break;
       case Op::LETTERBOX: { LetterboxParams q = op.lb; q.in = d_frames; rc = letterbox_launch(q, st); break; }
       case Op::STEM: { StemParams q = op.stem; if (!q.in) q.in = d_frames; rc = stem_launch(q, st); break; }
+      case Op::STEM_IM2COL:
+        rc = stem_im2col_launch(static_cast<const uint8_t*>(op.stem.in ? op.stem.in : d_frames), op.s_out.p, op.stem.B, op.stem.H,
+                                op.stem.W, st);
+        break;
       case Op::DECODE: { DecodeParams q = op.dec; q.raw = d_raw; rc = decode_launch(q, st); break; }
       case Op::POST: { PostParams q = op.post; q.out = d_out; rc = postprocess_launch(q, st); break; }
     }
@@ -598,7 +632,7 @@ static const char* op_kind_name(Op::Kind k) {
   switch (k) {
     case Op::GEMM: return "conv_gemm"; case Op::DIRECT: return "conv_direct"; case Op::AVGPAD: return "avgpool2_pad";
     case Op::AVGMAX: return "avgmax_pool"; case Op::MAXPOOL5: return "maxpool5"; case Op::UPSAMPLE: return "upsample2";
-    case Op::CBFUSE: return "cbfuse"; case Op::LETTERBOX: return "letterbox"; case Op::STEM: return "stem";
+    case Op::CBFUSE: return "cbfuse"; case Op::LETTERBOX: return "letterbox"; case Op::STEM: return "stem"; case Op::STEM_IM2COL: return "stem_im2col";
     case Op::DECODE: return "decode"; case Op::POST: return "postprocess";
   }
   return "?";

@@ -284,7 +284,8 @@ def _detect_fwd(P, q, pfx, xs, d):
     return torch.cat([dbox, torch.sigmoid(cls)], 1)
 
 
-def forward_raw(size: str, P: Dict[str, torch.Tensor], x: torch.Tensor, quant=None, taps: list | None = None) -> torch.Tensor:
+def forward_raw(size: str, P: Dict[str, torch.Tensor], x: torch.Tensor, quant=None, taps: list | None = None,
+                stem_int: bool = True) -> torch.Tensor:
     """x: (B,3,H,W) fp32 RGB in [0,1] -> (B,84,A). Mirrors the routing loop of YOLOv9.__call__ (:380-385)."""
     q = _Q(quant)
     spec = build_spec(size)
@@ -297,8 +298,14 @@ def forward_raw(size: str, P: Dict[str, torch.Tensor], x: torch.Tensor, quant=No
         pfx = f"model.{i}"
         op = l["op"]
         if op == "conv":
-            # the 3-channel stems keep fp32 weights on the CUDA path (CUDA-core kernel)
-            cur = _cv(P, q, pfx + ".conv", cur, s=l["s"], quant_w=(l["cin"] != 3))
+            if l["cin"] == 3 and q.mode == "bf16" and stem_int:
+                # uint8 frames on the CUDA path: exact integer pixels x bf16(w/255) on tensor cores
+                w = q.w(P[pfx + ".conv.weight"] / 255.0)
+                y = F.conv2d(torch.round(cur * 255.0), w, P[pfx + ".conv.bias"], stride=l["s"], padding=1)
+                cur = q.act(y * torch.sigmoid(y))
+            else:
+                # float frames: the 3-channel stems keep fp32 weights (CUDA-core kernel)
+                cur = _cv(P, q, pfx + ".conv", cur, s=l["s"], quant_w=(l["cin"] != 3))
         elif op == "elan4":
             cur = _elan4_fwd(P, q, pfx, cur, l["n"])
         elif op == "elan1":
@@ -465,7 +472,7 @@ def scale_boxes(img1_shape, preds, img0_shape):
     return out
 
 
-def detect(size: str, P, frames, res: int, quant=None, bgr_swap=True) -> torch.Tensor:
+def detect(size: str, P, frames, res: int, quant=None, bgr_swap=True, stem_int=None) -> torch.Tensor:
     """YOLOv9.__call__ (:375-388) for a batch of same-shape HWC BGR frames (uint8 or float32).
 
     Returns (B,300,6) [x1,y1,x2,y2,conf,cls] in original-frame pixels (the reference returns image 0 only)."""
@@ -475,7 +482,7 @@ def detect(size: str, P, frames, res: int, quant=None, bgr_swap=True) -> torch.T
     x = pre.flip(-1) if bgr_swap else pre
     x = x.permute(0, 3, 1, 2).to(torch.float32) / 255.0
     with torch.no_grad():
-        raw = forward_raw(size, P, x, quant=quant)
+        raw = forward_raw(size, P, x, quant=quant, stem_int=(frames.dtype == torch.uint8) if stem_int is None else stem_int)
         preds = postprocess(raw)
     return scale_boxes(pre.shape[1:3], preds, frames.shape[1:3])
 
