@@ -191,7 +191,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   uint64_t* afull_bar = bars + 2 * S + 4;     // halo mode (up to 4 stages)
   uint64_t* aempty_bar = bars + 2 * S + 8;
   uint64_t* bres_bar = bars + 2 * S + 12;     // resident-B mode
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 13);
+  uint64_t* res_bar = bars + 2 * S + 13;      // residual prefetch (one per staging buffer)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 15);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
@@ -212,6 +213,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       mbar_init(&aempty_bar[i], 1);
     }
     mbar_init(bres_bar, 1);
+    mbar_init(&res_bar[0], 1);
+    mbar_init(&res_bar[1], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -306,6 +309,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t pass_ctr = 0;   // staging passes issued so far (TMA-store double buffering)
+    const int passes_per_tile = (p.BN + CH - 1) / CH;
+    // residual prefetch (in-place residual through tmC): the TMA load of the residual sub-tiles of staging pass `k`
+    // lands in the buffer the pass will overwrite with its result; issued one pass ahead by thread et == 0
+    auto issue_res = [&](uint32_t k) {
+      const int t_idx = static_cast<int>(k) / passes_per_tile;                       // k-th pass of this CTA
+      const int tile_k = blockIdx.x + t_idx * gridDim.x;
+      if (tile_k >= p.num_tiles) return;
+      const int cc0k = (static_cast<int>(k) - t_idx * passes_per_tile) * CH;
+      const int chnk = (p.BN - cc0k) < CH ? (p.BN - cc0k) : CH;
+      const int nbk = tile_k % p.n_blocks, mk = tile_k / p.n_blocks;
+      const int w0k = (mk % p.tiles_w) << p.lTW, h0k = ((mk / p.tiles_w) % p.tiles_h) << p.lTH, n0k = (mk / tiles_wh) << p.lTN;
+      const int b = (p.stg_bufs == 2) ? (k & 1) : 0;
+      uint8_t* dstb = sStage + b * stg_bytes;
+      const int nsub = (chnk * es) >> 7;
+      mbar_arrive_expect_tx(&res_bar[b], nsub * (kTileM * 128));
+      for (int j = 0; j < nsub; ++j) {
+        const int cc = nbk * p.BN + cc0k + j * (128 / es);
+        if (p.halo) tma_load_5d(dstb + j * (kTileM * 128), &p.tmC, &res_bar[b], cc, w0k, n0k, h0k, 0);
+        else tma_load_5d(dstb + j * (kTileM * 128), &p.tmC, &res_bar[b], cc, w0k, h0k, n0k, 0);
+      }
+    };
+    if (p.res_tma == 1 && et == 0) issue_res(0);
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int nb = tile % p.n_blocks;
       const int m = tile / p.n_blocks;
@@ -329,11 +354,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         uint8_t* sbuf = sStage;
         if (p.tma_store) {
           if (p.stg_bufs == 2) sbuf += (pass_ctr & 1) * stg_bytes;
-          if (et == 0) {  // the buffer about to be overwritten must have been read by its TMA store
+          if (et == 0 && p.res_tma != 1) {  // the buffer about to be overwritten must have been read by its TMA store
             if (p.stg_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
           }
         }
-        named_bar_sync(1, kEpiThreads);                          // staging buffer free
+        if (p.res_tma == 1) {
+          // the residual tile has landed in this buffer (which also proves the buffer was free)
+          const uint32_t b = (p.stg_bufs == 2) ? (pass_ctr & 1) : 0;
+          const uint32_t par = (p.stg_bufs == 2) ? ((pass_ctr >> 1) & 1) : (pass_ctr & 1);
+          mbar_wait(&res_bar[b], par);
+        } else {
+          named_bar_sync(1, kEpiThreads);                        // staging buffer free
+        }
         for (int c = half * 16; c < chn; c += 16 * kColGroups) {
           uint32_t v[16];
           tmem_ld16(t_row + cc0 + c, v);
@@ -348,7 +380,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           float f[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = act_apply<ACT>(__uint_as_float(v[j]) + bia[j]);
-          if (p.res != nullptr && pvalid) {
+          if (p.res_tma == 2) {
+            // nothing to read: the TMA reduce-add store adds the residual in place
+          } else if (p.res_tma == 1) {
+            const uint32_t boff = c * es;
+            const uint8_t* sub = sbuf + (boff >> 7) * (kTileM * 128) + row * 128;
+            const uint32_t ch0 = (boff & 127) >> 4;
+            if (F32) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 r = *reinterpret_cast<const float4*>(sub + (((ch0 + j) ^ (row & 7)) << 4));
+                f[4 * j + 0] += r.x; f[4 * j + 1] += r.y; f[4 * j + 2] += r.z; f[4 * j + 3] += r.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const uint4 r = *reinterpret_cast<const uint4*>(sub + (((ch0 + j) ^ (row & 7)) << 4));
+                const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  f[8 * j + 2 * q + 0] += __uint_as_float(rr[q] << 16);
+                  f[8 * j + 2 * q + 1] += __uint_as_float(rr[q] & 0xFFFF0000u);
+                }
+              }
+            }
+          } else if (p.res != nullptr && pvalid) {
             if (F32) {
               const float4* r4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) +
                                                                  ppix * p.res_cs + p.res_co + gcol);
@@ -419,10 +475,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             const int col0 = nb * p.BN + cc0;
             for (int j = 0; j < nsub; ++j) {
               const int cc = col0 + j * (128 / es);
-              if (p.halo) tma_store_5d(&p.tmC, sbuf + j * (kTileM * 128), cc, w0, n0, h0, 0);
+              if (p.res_tma == 2) {   // out += tile (fp32 in-place residual, added at the L2)
+                if (p.halo) tma_reduce_add_5d(&p.tmC, sbuf + j * (kTileM * 128), cc, w0, n0, h0, 0);
+                else tma_reduce_add_5d(&p.tmC, sbuf + j * (kTileM * 128), cc, w0, h0, n0, 0);
+              } else if (p.halo) tma_store_5d(&p.tmC, sbuf + j * (kTileM * 128), cc, w0, n0, h0, 0);
               else tma_store_5d(&p.tmC, sbuf + j * (kTileM * 128), cc, w0, h0, n0, 0);
             }
             tma_store_commit();
+            if (p.res_tma == 1) {
+              // next pass's buffer: with two buffers its last store is one group older than the one just committed
+              if (p.stg_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+              issue_res(pass_ctr + 1);
+            }
           }
           ++pass_ctr;
           continue;
@@ -494,7 +558,8 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
   // ---- N blocking
   int BN = d.bn_override;
   if (BN == 0) {
-    const int maxbn = d.out_f32 ? 128 : 256;
+    static const int f32bn_env = getenv("CC_F32_BN") ? atoi(getenv("CC_F32_BN")) : 256;
+    const int maxbn = d.out_f32 ? f32bn_env : 256;   // fp32 output: 64-column staging passes, so 256-wide tiles fit too
     // largest multiple of 16 that divides Cout and fits the tile limit
     for (BN = (d.Cout < maxbn ? d.Cout : maxbn) & ~15; BN >= 16; BN -= 16)
       if (d.Cout % BN == 0) break;
@@ -615,7 +680,7 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
     // double-buffer the staging when the pipeline still gets >= 4 stages (per-tap mode) / 3 B stages (halo mode)
     const int one = kTileM * CH * es;
     const int stage_b = p.halo ? BN * p.BK * 2 : kTileM * p.BK * 2 + BN * p.BK * 2;
-    const int other = 1024 + d.Cout * 4 + 256;
+    const int other = 1024 + d.Cout * 4 + 320;
     if (!p.halo && (kMaxSmem - other - 2 * one) / stage_b >= 4) p.stg_bufs = 2;
     if (p.halo && kMaxSmem - other - 2 * one - 3 * stage_b >= 3 * p.halo_bytes) p.stg_bufs = 2;
     void* base = reinterpret_cast<uint8_t*>(d.out) + size_t(d.out_co) * es;
@@ -637,10 +702,13 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
                      CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     CC_REQUIRE(r == CUDA_SUCCESS, "conv_gemm: cuTensorMapEncodeTiled(C) failed: %d", int(r));
   }
+  static const int restma_env = getenv("CC_RES_TMA") ? atoi(getenv("CC_RES_TMA")) : 1;
+  p.res_tma = (restma_env && p.tma_store && d.res != nullptr && d.res == d.out && d.res_cs == d.out_cs && d.res_co == d.out_co) ? 1 : 0;
+  if (p.res_tma && d.out_f32 && restma_env >= 1 && restma_env != 3) p.res_tma = 2;   // fp32: reduce-add store (CC_RES_TMA=3 forces the prefetch variant)
   const int pitch = p.tma_store ? CH * es : CH * es + 16;
   const int staging = ((kTileM * pitch + 15) & ~15) * (p.tma_store ? p.stg_bufs : 1);
   const int stage_bytes = kTileM * p.BK * 2 + BN * p.BK * 2;
-  const int fixed = 1024 /*align slack*/ + staging + d.Cout * 4 /*bias*/ + 256 /*barriers*/;
+  const int fixed = 1024 /*align slack*/ + staging + d.Cout * 4 /*bias*/ + 320 /*barriers*/;
   int S;
   static const int bres_env = getenv("CC_BRES") ? atoi(getenv("CC_BRES")) : 1;
   static const int hst_env = getenv("CC_HALO_STAGES") ? atoi(getenv("CC_HALO_STAGES")) : 0;

@@ -46,6 +46,7 @@ struct GemmParams {
   int32_t halo_stages;                // 2..4 halo buffers in flight
   int32_t tma_store, stg_bufs;        // epilogue stores through TMA from 128B-swizzled staging (1 or 2 buffers)
   int32_t b_res;                      // weights of the (single) N block stay resident in smem for the whole kernel
+  int32_t res_tma;                    // in-place residual is prefetched into the staging buffer by TMA (through tmC)
 };
 
 struct ConvDesc {
