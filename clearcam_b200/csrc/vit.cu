@@ -259,8 +259,17 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+static constexpr int kAttnWarps = 5;    // warps per CTA
+static constexpr int kAttnSplitMax = 2; // CTAs per (image, head) for long sequences: each takes half of the 16-query blocks
+
 template <bool CAUSAL>
-__global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ ctx,
+__global__ void __launch_bounds__(32 * kAttnWarps) attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ ctx,
                                                         int L, int H) {
   extern __shared__ __align__(16) __nv_bfloat16 smem_attn[];
   const int W = H * 64;
@@ -287,7 +296,9 @@ __global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __r
   const int g = lane >> 2, t4 = lane & 3;
   const float kLog2e = 1.4426950408889634f;
 
-  for (int qb = warp; qb * 16 < L; qb += 4) {
+  const int nqb = (L + 15) / 16, per = (nqb + gridDim.y - 1) / gridDim.y;
+  const int qb_lo = blockIdx.y * per, qb_hi = (qb_lo + per < nqb) ? qb_lo + per : nqb;
+  for (int qb = qb_lo + warp; qb < qb_hi; qb += kAttnWarps) {
     const int r0 = qb * 16 + g, r1 = r0 + 8;
     // Q fragments, pre-scaled by 1/sqrt(64) = 2^-3 (exact in bf16)
     uint32_t qa[4][4];
@@ -338,18 +349,23 @@ __global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __r
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
       const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
       // rows that are pure padding (r >= L) see only finite zeros; every real row has key 0 unmasked -> mn finite
-      const float a0 = exp2f((m0 - mn0) * kLog2e), a1 = exp2f((m1 - mn1) * kLog2e);
-      m0 = mn0; m1 = mn1;
+      const bool grew = (mn0 != m0) | (mn1 != m1);
+      const float c0 = mn0 * kLog2e, c1 = mn1 * kLog2e;
       float p[2][4];
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt) {
-        p[nt][0] = exp2f((s[nt][0] - mn0) * kLog2e); p[nt][1] = exp2f((s[nt][1] - mn0) * kLog2e);
-        p[nt][2] = exp2f((s[nt][2] - mn1) * kLog2e); p[nt][3] = exp2f((s[nt][3] - mn1) * kLog2e);
+        p[nt][0] = fast_exp2(fmaf(s[nt][0], kLog2e, -c0)); p[nt][1] = fast_exp2(fmaf(s[nt][1], kLog2e, -c0));
+        p[nt][2] = fast_exp2(fmaf(s[nt][2], kLog2e, -c1)); p[nt][3] = fast_exp2(fmaf(s[nt][3], kLog2e, -c1));
       }
-      l0 = l0 * a0 + p[0][0] + p[0][1] + p[1][0] + p[1][1];
-      l1 = l1 * a1 + p[0][2] + p[0][3] + p[1][2] + p[1][3];
+      if (__any_sync(0xffffffffu, grew)) {   // the running maximum moved for some row of this warp: rescale
+        const float a0 = fast_exp2((m0 - mn0) * kLog2e), a1 = fast_exp2((m1 - mn1) * kLog2e);
+        l0 *= a0; l1 *= a1;
 #pragma unroll
-      for (int d = 0; d < 8; ++d) { o[d][0] *= a0; o[d][1] *= a0; o[d][2] *= a1; o[d][3] *= a1; }
+        for (int d = 0; d < 8; ++d) { o[d][0] *= a0; o[d][1] *= a0; o[d][2] *= a1; o[d][3] *= a1; }
+      }
+      m0 = mn0; m1 = mn1;
+      l0 += p[0][0] + p[0][1] + p[1][0] + p[1][1];
+      l1 += p[0][2] + p[0][3] + p[1][2] + p[1][3];
       const uint32_t pa[4] = {pack2(p[0][0], p[0][1]), pack2(p[0][2], p[0][3]), pack2(p[1][0], p[1][1]), pack2(p[1][2], p[1][3])};
       // P.V: B fragments of V via ldmatrix.trans (two 8-wide d tiles per instruction)
 #pragma unroll
@@ -387,8 +403,9 @@ int attention_launch(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, int B, int L,
     CC_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  if (causal) attention_kernel<true><<<B * H, 128, smem, st>>>(qkv, ctx, L, H);
-  else attention_kernel<false><<<B * H, 128, smem, st>>>(qkv, ctx, L, H);
+  const dim3 grid(B * H, ((L + 15) / 16 > 2 * kAttnWarps) ? kAttnSplitMax : 1);   // short sequences: one CTA stages K/V once
+  if (causal) attention_kernel<true><<<grid, 32 * kAttnWarps, smem, st>>>(qkv, ctx, L, H);
+  else attention_kernel<false><<<grid, 32 * kAttnWarps, smem, st>>>(qkv, ctx, L, H);
   CC_CHECK_CUDA(cudaGetLastError());
   return CC_OK;
 }
