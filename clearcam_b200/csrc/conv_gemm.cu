@@ -228,9 +228,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // PDL: everything above (barrier init, TMEM alloc, descriptor prefetch, bias -> smem: weights only) overlapped the
-  // tail of the previous kernel; activations of the previous layer are only touched after this point.
-  pdl_wait();
+  // PDL: let the next kernel start its prologue as our CTAs retire; everything that only touches WEIGHTS (bias above,
+  // resident / first weight tiles below) runs before griddepcontrol.wait, i.e. overlaps the previous kernel's tail.
+  // Activations of the previous layer are read only by the TMA producer (A operand) and the epilogue (residual):
+  // both execute pdl_wait() first.
   pdl_trigger();
 
   const int num_kb = p.num_taps * p.chunks_per_tap;
@@ -241,10 +242,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
-      if (p.b_res) {   // weights are not produced by the previous kernel: may be issued before/after pdl_wait alike
+      if (p.b_res) {   // weights are not produced by the previous kernel: issued BEFORE the grid dependency wait
         mbar_arrive_expect_tx(bres_bar, num_kb_all * b_bytes);
         for (int kb = 0; kb < num_kb_all; ++kb) tma_load_2d(sB + kb * b_bytes, &p.tmB, bres_bar, kb * p.BK, 0);
       }
+      pdl_wait();
       if (p.halo) {
         int sa = 0;
         uint32_t pa = 0;
@@ -330,6 +332,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         else tma_load_5d(dstb + j * (kTileM * 128), &p.tmC, &res_bar[b], cc, w0k, h0k, n0k, 0);
       }
     };
+    pdl_wait();   // residual reads below depend on the previous kernel's output
     if (p.res_tma == 1 && et == 0) issue_res(0);
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int nb = tile % p.n_blocks;
@@ -516,7 +519,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
   }
 
-  if (p.tma_store && threadIdx.x == 128) tma_store_wait_all();   // all bulk stores of this CTA have landed before it retires
+  if (p.tma_store && threadIdx.x == 128) tma_store_wait_read<0>();   // smem must outlive the bulk stores' reads (global completion is tracked by the grid)
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
