@@ -15,6 +15,7 @@
 #include "conv_gemm.cuh"
 #include "cc_common.h"
 #include "cc_ptx.cuh"
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -566,9 +567,34 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
     // largest multiple of 16 that divides Cout and fits the tile limit
     for (BN = (d.Cout < maxbn ? d.Cout : maxbn) & ~15; BN >= 16; BN -= 16)
       if (d.Cout % BN == 0) break;
-    // if the machine would be under-filled, halve the N tile (more, smaller tiles)
     const long long mt = (static_cast<long long>(d.N) * Hout * Wout + 127) / 128;
-    while (BN > 64 && (BN / 2) % 16 == 0 && mt * (d.Cout / BN) < num_sms) BN /= 2;
+    static const int bnmodel_env = getenv("CC_BN_MODEL") ? atoi(getenv("CC_BN_MODEL")) : 2;
+    // measured (same-box A/B): the model helps the fp32-output GEMMs of the ViT (+7 % ViT-B/32) and costs the bf16
+    // conv stack 1 %, so by default it is applied to fp32 outputs only (1 = everywhere, 0 = never)
+    if (bnmodel_env == 1 || (bnmodel_env == 2 && d.out_f32)) {
+      // pick the N tile by a small cost model: rounds over the SMs x per-tile time, where a tile costs the larger of its
+      // MMA time (2*BN cycles per 64-deep k-block, ~160-cycle issue floor) and its L2->SM load time, plus the epilogue
+      const int bk = (d.Cin % 64 == 0) ? 64 : (d.Cin % 32 == 0 ? 32 : 16);
+      const double nkb = double(d.k) * d.k * d.Cin / bk;
+      double best_cost = 1e30;
+      int best_bn = BN;
+      for (int bn = (d.Cout < maxbn ? d.Cout : maxbn) & ~15; bn >= 16; bn -= 16) {
+        if (d.Cout % bn) continue;
+        const double tiles = double(mt) * (d.Cout / bn);
+        const double rounds = ceil(tiles / num_sms);
+        const double mma = nkb * (2.0 * bn > 160 ? 2.0 * bn : 160.0) * bk / 64.0;
+        const double a_bytes = (d.k == 3 && d.stride == 1 && bk >= 32) ? 128.0 * bk * 2 * 2.25 / 9 : 128.0 * bk * 2;  // halo re-use
+        const double load = nkb * (a_bytes + bn * bk * 2.0) / 40.0;
+        const double epi = bn * 10.0 + 600.0;
+        const double tile = (mma > load ? mma : load);
+        const double cost = rounds * (tile > epi ? tile : epi) + epi + 3000.0;
+        if (cost < best_cost * 0.999) { best_cost = cost; best_bn = bn; }
+      }
+      BN = best_bn;
+    } else {
+      // if the machine would be under-filled, halve the N tile (more, smaller tiles)
+      while (BN > 64 && (BN / 2) % 16 == 0 && mt * (d.Cout / BN) < num_sms) BN /= 2;
+    }
   }
   CC_REQUIRE(BN % 16 == 0 && BN >= 16 && BN <= 256 && d.Cout % BN == 0, "conv_gemm: bad BN=%d for Cout=%d", BN, d.Cout);
   p.BN = BN;
