@@ -165,3 +165,19 @@ def test_shard_range_partitions():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_fp32_noise_floor_of_the_reference_arithmetic():
+    """The north-star bar (boxes within 1e-3 px of the fp32 path) is below what fp32 arithmetic itself reproduces:
+    the SAME oracle on the reference's real YOLOv9-t weights and a real frame moves boxes by more than 1e-3 px when
+    only the summation precision/order changes (fp32 vs fp64 accumulate).  Class probabilities stay within 1e-4."""
+    z = np.load(os.path.join(GOLD, "yolov9t_mot16.npz"))
+    P = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w:")}
+    pre = o.preprocess(torch.from_numpy(z["frame"]), 640)
+    x = pre.flip(-1).permute(2, 0, 1).unsqueeze(0).float() / 255
+    with torch.no_grad():
+        r32 = o.forward_raw("t", P, x)
+        r64 = o.forward_raw("t", {k: v.double() for k, v in P.items()}, x.double())
+    d = (r32.double() - r64).abs()
+    assert d[:, :4].max() > 1e-3, "fp32 and fp64 evaluation agree to 1e-3 px?"
+    assert d[:, :4].mean() < 1e-3 and d[:, 4:].max() < 1e-4
