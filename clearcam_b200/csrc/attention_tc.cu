@@ -1,0 +1,300 @@
+// Multi-head attention on tcgen05 (sm_100a), d_head = 64:  ctx = softmax(Q K^T / 8 [+ causal mask]) V per (image, head).
+// Reference: models/objects.py:108-118 (image tower), :157-168 (text tower, causal).
+//
+// One CTA per (image, head); K and V^T of the head are TMA-loaded once, then the CTA walks the 128-query blocks:
+//   S[128 x Lk]  = Q[128 x 64] . K[Lk x 64]^T      tcgen05.mma, accumulators in TMEM columns [0, Lk)
+//   softmax      : 4 warps, thread == query row, two passes over TMEM (row max, then exp2/sum); P (bf16, unnormalised,
+//                  <= 1) is written straight into the 128B-swizzled K-major layout the second MMA reads as its A operand
+//   O[128 x 64]  = P[128 x Lk] . Vt[64 x Lk]^T     tcgen05.mma, accumulators in the 64 TMEM columns after S
+//   ctx          = O / rowsum  -> bf16
+// V is consumed as a K-major B operand, so a small pre-pass writes V^T per head ([B*H*64, Lk], keys contiguous,
+// zero padded to Lk = ceil(L/64)*64); Q and K are read in place from the fused QKV buffer through one 2-D tensor map.
+#include "ops.cuh"
+#include "cc_common.h"
+#include "cc_ptx.cuh"
+#include <stdlib.h>
+
+namespace cc {
+
+static constexpr int kMaxLk = 448;   // S uses TMEM columns [0, Lk), O the 64 columns after it: Lk + 64 <= 512
+
+struct AttnParams {
+  CUtensorMap tmQK;   // qkv viewed as [B*L rows][3W cols], box 64 rows x 64 cols
+  CUtensorMap tmVt;   // Vt [B*H*64 rows][Lk cols], box 64 rows x 64 cols
+  __nv_bfloat16* ctx;
+  int B, L, Lk, H, W, causal;
+  int tmem_cols;   // power of two >= Lk + 64
+};
+
+// ---------------------------------------------------------------- V^T pre-pass
+__global__ void __launch_bounds__(256) vt_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ vt, int L,
+                                                 int Lk, int H, int W) {
+  __shared__ __nv_bfloat16 tile[64][66];
+  const int bh = blockIdx.x, b = bh / H, h = bh % H;
+  const int t0 = blockIdx.y * 64;
+  const __nv_bfloat16* src = qkv + static_cast<long long>(b) * L * 3 * W + 2 * W + h * 64;
+  for (int i = threadIdx.x; i < 64 * 8; i += 256) {   // 64 tokens x 8 chunks of 8 d
+    const int t = i >> 3, c = (i & 7) * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (t0 + t < L) v = __ldg(reinterpret_cast<const uint4*>(src + static_cast<long long>(t0 + t) * 3 * W + c));
+    const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tile[t][c + j] = e[j];
+  }
+  __syncthreads();
+  __nv_bfloat16* dst = vt + static_cast<long long>(bh) * 64 * Lk + t0;
+  for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+    const int d = i >> 6, t = i & 63;
+    dst[static_cast<long long>(d) * Lk + t] = tile[t][d];
+  }
+}
+
+// ---------------------------------------------------------------- main kernel
+__global__ void __launch_bounds__(160) attention_tc_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = p.Lk >> 6;                       // 64-key blocks
+  uint8_t* sQ = smem;                              // [128][128 B]
+  uint8_t* sK = sQ + 128 * 128;                    // [Lk][128 B]
+  uint8_t* sV = sK + p.Lk * 128;                   // nkb x [64 d][128 B]
+  uint8_t* sP = sV + nkb * 8192;                   // nkb x [128 rows][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + nkb * 16384);
+  uint64_t* bar_k = bars;        // K landed
+  uint64_t* bar_v = bars + 1;    // V^T landed
+  uint64_t* bar_q = bars + 2;    // Q block landed            (phase per q-block)
+  uint64_t* bar_s = bars + 3;    // S = QK^T complete
+  uint64_t* bar_p = bars + 4;    // P written (128 arrivals)
+  uint64_t* bar_o = bars + 5;    // O = PV complete
+  uint64_t* bar_oe = bars + 6;   // O read back (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+
+  const int bh = blockIdx.x, b = bh / p.H, h = bh % p.H;
+  const int nqb = (p.L + 127) >> 7;
+  const uint32_t kOCol = p.Lk;                    // O accumulator right after S
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&p.tmQK);
+      tma_prefetch_desc(&p.tmVt);
+      mbar_init(bar_k, 1); mbar_init(bar_v, 1); mbar_init(bar_q, 1); mbar_init(bar_s, 1);
+      mbar_init(bar_p, 128); mbar_init(bar_o, 1); mbar_init(bar_oe, 128);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== control warp: TMA loads + MMA issue (one elected lane) =====================
+    const int row0 = b * p.L;
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_k, p.Lk * 128);
+      for (int j = 0; j < nkb; ++j) tma_load_2d(sK + j * 8192, &p.tmQK, bar_k, p.W + h * 64, row0 + 64 * j);
+      mbar_arrive_expect_tx(bar_v, nkb * 8192);
+      for (int j = 0; j < nkb; ++j) tma_load_2d(sV + j * 8192, &p.tmVt, bar_v, 64 * j, bh * 64);
+      mbar_arrive_expect_tx(bar_q, 128 * 128);
+      tma_load_2d(sQ, &p.tmQK, bar_q, h * 64, row0);
+      tma_load_2d(sQ + 8192, &p.tmQK, bar_q, h * 64, row0 + 64);
+    }
+    __syncwarp();
+    const int nch = (p.Lk + 255) >> 8;             // N chunks of the first MMA (N <= 256 each)
+    const int chN = p.Lk / nch;
+    const uint32_t idesc_s = umma_idesc_f16(128, chN, 1);
+    const uint32_t idesc_o = umma_idesc_f16(128, 64, 1);
+    const uint64_t dconst = (1ull << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+    const uint32_t q16 = (smem_u32(sQ) & 0x3FFFF) >> 4, k16 = (smem_u32(sK) & 0x3FFFF) >> 4;
+    const uint32_t v16 = (smem_u32(sV) & 0x3FFFF) >> 4, p16 = (smem_u32(sP) & 0x3FFFF) >> 4;
+    mbar_wait(bar_k, 0);
+    for (int qb = 0; qb < nqb; ++qb) {
+      const uint32_t ph = qb & 1;
+      mbar_wait(bar_q, ph);
+      tc_fence_after();
+      if (elect_one()) {
+        for (int c = 0; c < nch; ++c) {
+          const uint64_t bd = dconst | (k16 + ((c * chN * 128) >> 4));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (k == 0) umma_f16_c<false>(tmem_base + c * chN, dconst | q16, bd, idesc_s);
+            else umma_f16_c<true>(tmem_base + c * chN, (dconst | q16) + 2 * k, bd + 2 * k, idesc_s);
+          }
+        }
+        umma_commit(bar_s);
+      }
+      __syncwarp();
+      mbar_wait(bar_p, ph);          // P ready (=> S fully read, first MMA long done: Q buffer is free)
+      tc_fence_after();
+      if (qb + 1 < nqb && lane == 0) {
+        mbar_arrive_expect_tx(bar_q, 128 * 128);
+        tma_load_2d(sQ, &p.tmQK, bar_q, h * 64, row0 + 128 * (qb + 1));
+        tma_load_2d(sQ + 8192, &p.tmQK, bar_q, h * 64, row0 + 128 * (qb + 1) + 64);
+      }
+      __syncwarp();
+      if (qb == 0) mbar_wait(bar_v, 0);
+      else mbar_wait(bar_oe, ph ^ 1);   // previous O has been read back
+      tc_fence_after();
+      if (elect_one()) {
+        for (int kb = 0; kb < nkb; ++kb) {
+          const uint64_t ad = dconst | (p16 + kb * (16384 >> 4));
+          const uint64_t bd = dconst | (v16 + kb * (8192 >> 4));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (kb == 0 && k == 0) umma_f16_c<false>(tmem_base + kOCol, ad, bd, idesc_o);
+            else umma_f16_c<true>(tmem_base + kOCol, ad + 2 * k, bd + 2 * k, idesc_o);
+          }
+        }
+        umma_commit(bar_o);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== softmax / epilogue warps (thread == query row) =====================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const float kScale = 0.125f * 1.4426950408889634f;   // 1/sqrt(64) * log2(e)
+    for (int qb = 0; qb < nqb; ++qb) {
+      const uint32_t ph = qb & 1;
+      const int qi = qb * 128 + row;              // query index inside the sequence
+      const int lim = p.causal ? (qi < p.L - 1 ? qi : p.L - 1) : p.L - 1;   // last visible key
+      mbar_wait(bar_s, ph);
+      tc_fence_after();
+      float m = -INFINITY;
+      for (int c0 = 0; c0 < p.Lk; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_row + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (c0 + j <= lim) m = fmaxf(m, __uint_as_float(v[j]));
+      }
+      const float mc = m * kScale;
+      float sum = 0.f;
+      for (int c0 = 0; c0 < p.Lk; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_row + c0, v);
+        tmem_ld_wait();
+        float e[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float x;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(x) : "f"(fmaf(__uint_as_float(v[j]), kScale, -mc)));
+          e[j] = (c0 + j <= lim) ? x : 0.f;
+          sum += e[j];
+        }
+        uint8_t* blk = sP + (c0 >> 6) * 16384 + row * 128;
+        const uint32_t i0 = (c0 & 63) >> 3;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          uint32_t w[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            __nv_bfloat162 hh = __floats2bfloat162_rn(e[8 * q + 2 * j], e[8 * q + 2 * j + 1]);
+            w[j] = *reinterpret_cast<uint32_t*>(&hh);
+          }
+          *reinterpret_cast<uint4*>(blk + (((i0 + q) ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_p);
+      // ---- O -> ctx
+      mbar_wait(bar_o, ph);
+      tc_fence_after();
+      const float inv = 1.0f / sum;
+      __nv_bfloat16* out = p.ctx + (static_cast<long long>(b) * p.L + qi) * p.W + h * 64;
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_row + kOCol + c0, v);
+        tmem_ld_wait();
+        if (qi < p.L) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            uint32_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              __nv_bfloat162 hh = __floats2bfloat162_rn(__uint_as_float(v[8 * q + 2 * j]) * inv,
+                                                        __uint_as_float(v[8 * q + 2 * j + 1]) * inv);
+              w[j] = *reinterpret_cast<uint32_t*>(&hh);
+            }
+            *reinterpret_cast<uint4*>(out + c0 + 8 * q) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_oe);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------- host
+bool attention_tc_supported(int L) {
+  // CC_ATTN_TC: 0 = never, 1 (default) = where it wins on B200 (more than one 128-query block: ViT-L/14's 257 tokens;
+  // the 50- and 77-token sequences stay on the mma.sync kernel, measured 25 % faster there), 2 = wherever it fits.
+  // Read when a plan is built, so tests can force either path.
+  const char* e = getenv("CC_ATTN_TC");
+  const int mode = e ? atoi(e) : 1;
+  const int Lk = (L + 63) / 64 * 64;
+  if (mode == 0 || Lk > kMaxLk) return false;
+  return mode >= 2 || L > 128;
+}
+size_t attention_tc_workspace_bytes(int B, int L, int H) {
+  const int Lk = (L + 63) / 64 * 64;
+  return static_cast<size_t>(B) * H * 64 * Lk * 2;
+}
+
+int attention_tc_launch(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, __nv_bfloat16* vt_ws, int B, int L, int H, int causal,
+                        cudaStream_t st) {
+  if (B == 0) return CC_OK;
+  const int W = H * 64, Lk = (L + 63) / 64 * 64, nkb = Lk / 64;
+  CC_REQUIRE(Lk <= kMaxLk, "attention_tc: sequence length %d too long", L);
+  PFN_encodeTiled enc = get_encode_tiled();
+  CC_REQUIRE(enc != nullptr, "attention_tc: cuTensorMapEncodeTiled unavailable");
+  AttnParams p{};
+  p.ctx = ctx; p.B = B; p.L = L; p.Lk = Lk; p.H = H; p.W = W; p.causal = causal;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < Lk + 64) p.tmem_cols <<= 1;
+  {
+    cuuint64_t dims[2] = {cuuint64_t(3) * W, cuuint64_t(B) * L};
+    cuuint64_t strides[1] = {cuuint64_t(3) * W * 2};
+    cuuint32_t box[2] = {64, 64}, estr[2] = {1, 1};
+    CUresult r = enc(&p.tmQK, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(qkv), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CC_REQUIRE(r == CUDA_SUCCESS, "attention_tc: tensor map (QK) failed: %d", int(r));
+  }
+  {
+    cuuint64_t dims[2] = {cuuint64_t(Lk), cuuint64_t(B) * H * 64};
+    cuuint64_t strides[1] = {cuuint64_t(Lk) * 2};
+    cuuint32_t box[2] = {64, 64}, estr[2] = {1, 1};
+    CUresult r = enc(&p.tmVt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, vt_ws, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CC_REQUIRE(r == CUDA_SUCCESS, "attention_tc: tensor map (Vt) failed: %d", int(r));
+  }
+  vt_kernel<<<dim3(B * H, nkb), 256, 0, st>>>(qkv, vt_ws, L, Lk, H, W);
+  CC_CHECK_CUDA(cudaGetLastError());
+  const int smem = 1024 + 128 * 128 + Lk * 128 + nkb * 8192 + nkb * 16384 + 128;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CC_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  attention_tc_kernel<<<B * H, 160, smem, st>>>(p);
+  CC_CHECK_CUDA(cudaGetLastError());
+  return CC_OK;
+}
+
+}  // namespace cc

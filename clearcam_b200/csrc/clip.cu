@@ -33,7 +33,7 @@ struct VOp {
   // generic slots
   const float* f0 = nullptr; const float* f1 = nullptr; const float* f2 = nullptr; const float* f3 = nullptr;
   float* fo = nullptr;
-  __nv_bfloat16* bo = nullptr; const __nv_bfloat16* bi = nullptr;
+  __nv_bfloat16* bo = nullptr; const __nv_bfloat16* bi = nullptr; __nv_bfloat16* bw = nullptr;
   const int* idx = nullptr; int* io = nullptr;
   int i0 = 0, i1 = 0, i2 = 0, i3 = 0, i4 = 0;
   long long l0 = 0;
@@ -156,11 +156,12 @@ struct PlanBuilder {
     __nv_bfloat16* qkv = static_cast<__nv_bfloat16*>(dalloc(static_cast<size_t>(rows) * 3 * W * 2));
     __nv_bfloat16* ctx = static_cast<__nv_bfloat16*>(dalloc(static_cast<size_t>(rows) * W * 2));
     __nv_bfloat16* hid = static_cast<__nv_bfloat16*>(dalloc(static_cast<size_t>(rows) * tw.mlp * 2));
+    __nv_bfloat16* vt = attention_tc_supported(L) ? static_cast<__nv_bfloat16*>(dalloc(attention_tc_workspace_bytes(B, L, tw.heads))) : nullptr;
     for (int i = 0; i < tw.layers && !rc; ++i) {
       const BlockW& b = bw[i];
       { VOp op; op.kind = VOp::LN; op.name = "ln_1"; op.f0 = x; op.bo = h; op.f1 = b.ln1_g; op.f2 = b.ln1_b; op.i0 = rows; op.i1 = W; op.l0 = 1; P.ops.push_back(op); }
       gemm("qkv", h, W, rows, W, b.w_in, b.b_in, 3 * W, qkv, 3 * W, false, CC_ACT_NONE, nullptr);
-      { VOp op; op.kind = VOp::ATTN; op.name = "attention"; op.bi = qkv; op.bo = ctx; op.i0 = B; op.i1 = L; op.i2 = tw.heads; op.i3 = causal ? 1 : 0;
+      { VOp op; op.kind = VOp::ATTN; op.name = "attention"; op.bi = qkv; op.bo = ctx; op.bw = vt; op.i0 = B; op.i1 = L; op.i2 = tw.heads; op.i3 = causal ? 1 : 0;
         op.flops = 4.0 * B * tw.heads * double(L) * L * 64; P.flops += op.flops; P.ops.push_back(op); }
       gemm("out_proj", ctx, W, rows, W, b.w_out, b.b_out, W, x, W, true, CC_ACT_NONE, x);
       { VOp op; op.kind = VOp::LN; op.name = "ln_2"; op.f0 = x; op.bo = h; op.f1 = b.ln2_g; op.f2 = b.ln2_b; op.i0 = rows; op.i1 = W; op.l0 = 1; P.ops.push_back(op); }
@@ -213,7 +214,10 @@ static int run_plan(ClipPlan& P, const void* d_in, float* d_out, long long out_s
       case VOp::GEMM: rc = conv_gemm_launch(op.gemm, st); break;
       case VOp::EMBED_LN: rc = embed_ln_pre_launch(op.fo, op.f0, op.f1, op.f2, op.f3, op.i0, op.i1, op.i2, st); break;
       case VOp::LN: rc = layernorm_bf16_launch(op.f0, op.bo, op.f1, op.f2, op.i0, op.i1, op.l0, op.idx, st); break;
-      case VOp::ATTN: rc = attention_launch(op.bi, op.bo, op.i0, op.i1, op.i2, op.i3, st); break;
+      case VOp::ATTN:
+        rc = op.bw ? attention_tc_launch(op.bi, op.bo, op.bw, op.i0, op.i1, op.i2, op.i3, st)
+                   : attention_launch(op.bi, op.bo, op.i0, op.i1, op.i2, op.i3, st);
+        break;
       case VOp::TEXT_EMBED: rc = text_embed_launch(static_cast<const int*>(d_in), op.f0, op.f1, op.fo, op.io, op.i0, op.i1, op.i2, op.i3, st); break;
       case VOp::L2NORM: rc = l2norm_launch(op.f0, d_out, op.i0, op.i1, out_stride, op.eps, st); break;
     }

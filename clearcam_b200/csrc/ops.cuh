@@ -93,6 +93,11 @@ int text_embed_launch(const int* ids, const float* tok, const float* pos, float*
                       int vocab, cudaStream_t st);
 int l2norm_launch(const float* in, float* out, int rows, int D, long long out_stride, float eps, cudaStream_t st);
 int attention_launch(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, int B, int L, int H, int causal, cudaStream_t st);
+// tcgen05 attention (attention_tc.cu); vt_ws: workspace of attention_tc_workspace_bytes() for the per-head V^T copy
+bool attention_tc_supported(int L);
+size_t attention_tc_workspace_bytes(int B, int L, int H);
+int attention_tc_launch(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, __nv_bfloat16* vt_ws, int B, int L, int H, int causal,
+                        cudaStream_t st);
 int search_scores_launch(const float* index, const float* q, float* scores, int N, int D, int Q, cudaStream_t st);
 
 }  // namespace cc

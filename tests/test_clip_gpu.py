@@ -16,6 +16,13 @@ PROMPTS = ["ferrari f40", "text here", "a photo of a cat", "person riding a bicy
            "delivery driver carrying a box", "dog"]
 
 
+@pytest.fixture(params=["0", "2"], ids=["attn-mma.sync", "attn-tcgen05"])
+def attn_mode(request, monkeypatch):
+    """Both attention kernels at every sequence length (CC_ATTN_TC is read when a plan is built; default 1 picks by shape)."""
+    monkeypatch.setenv("CC_ATTN_TC", request.param)
+    return request.param
+
+
 def _check(got: torch.Tensor, want: torch.Tensor):
     cos = (got * want).sum(-1) / (got.norm(dim=-1) * want.norm(dim=-1))
     assert cos.min() >= 0.999, f"cosine {cos.min()}"
@@ -28,7 +35,7 @@ def _check(got: torch.Tensor, want: torch.Tensor):
 
 
 @pytest.mark.parametrize("arch,B", [("ViT-tiny", 5), ("ViT-B/32", 6), ("ViT-B/32", 1), ("ViT-L/14", 3)])
-def test_image_encoder(arch, B):
+def test_image_encoder(arch, B, attn_mode):
     cfg = oc.CONFIGS[arch]
     P = oc.synthetic_weights(cfg, seed=3)
     x = oc.synthetic_images(B, cfg.image_size, seed=5)
@@ -41,7 +48,7 @@ def test_image_encoder(arch, B):
 
 
 @pytest.mark.parametrize("arch", ["ViT-tiny", "ViT-B/32", "ViT-L/14"])
-def test_text_encoder(arch):
+def test_text_encoder(arch, attn_mode):
     cfg = oc.CONFIGS[arch]
     P = oc.synthetic_weights(cfg, seed=4)
     m = OpenCLIP(weights=P, arch=arch)
