@@ -124,6 +124,25 @@ int cc_clip_profile(cc_clip* h, int text, const void* d_in, int B, float* d_out,
 /* ObjectFinder.search inner loop (models/objects.py:365-376): d_scores[q*N + n] = <d_index[n,:], d_q[q,:]>, fp32. */
 int cc_search_scores(const float* d_index, int N, int D, const float* d_q, int Q, float* d_scores, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Tracker that consumes the detector rows (host code, no GPU): ocsort_tracker/ocsort.py:163-308 `OCSort`, with
+ * association.py and kalmanfilter.py.  One handle per camera (clearcam.py:239 `ocsort.OCSort(max_age=100)`).
+ * cc_ocsort_create arguments = OCSort.__init__'s (ocsort.py:164-165; det_thresh is per update call as in :177).
+ * Track ids start at 1 per handle (the reference shares one class-level counter between cameras and resets it whenever
+ * any tracker is constructed, ocsort.py:177 — ids there are only unique per camera between such resets). */
+typedef struct cc_ocsort* cc_ocsort_t;
+int cc_ocsort_create(int max_age, int min_hits, double iou_threshold, int delta_t, double inertia, int use_byte, cc_ocsort_t* out);
+int cc_ocsort_destroy(cc_ocsort_t h);
+/* OCSort.update(output_results, det_thresh) (ocsort.py:177-308).  rows: host float32 [n,6] = x1,y1,x2,y2,score,class
+ * (the detector's (300,6) block as is; zero rows are ignored by the score gates).  out: host float64 [cap,9] =
+ * tl_x, tl_y, w, h, score, class_id, track_id, tracklet_len, speed — the STrack fields clearcam.py:583-621 reads —
+ * in the reference's order (newest track first).  *n_out = rows written; error if it would exceed cap. */
+int cc_ocsort_update(cc_ocsort_t h, const float* rows, int n, float det_thresh, double* out, int cap, int* n_out);
+/* The same for B cameras in one call: hs[B] (NULL entries skipped), rows [B,n,6], det_thresh [B], out [B,cap,9], n_out [B]. */
+int cc_ocsort_update_batch(cc_ocsort_t* hs, int B, const float* rows, int n, const float* det_thresh, double* out, int cap,
+                           int* n_out);
+int cc_ocsort_num_tracks(cc_ocsort_t h);
+
 #ifdef __cplusplus
 }
 #endif
