@@ -1,0 +1,106 @@
+"""All cameras in one detector call.
+
+The reference walks its cameras round-robin and runs the detector on one frame at a time (`VideoCapture.start`,
+clearcam.py:270-271 -> `process_frame` :423-461 -> `run_inference` :580-586: Tensor(frame) -> jit_infer(model) ->
+.numpy() -> tracker.update).  On a B200 a single 1080p frame leaves the GPU mostly idle, so `CameraBatch.step` takes the
+latest frame of every camera, groups the frames by shape (cameras differ in resolution; the detector's letterbox plan is
+per input shape), runs ONE `detect_batch` per group with uploads and result reads queued back to back, waits once, and
+then steps every camera's tracker in one library call.  What comes back per camera is what `run_inference` computes up
+to clearcam.py:589 — the (300,6) detector rows and the tracker's targets; zones, alerts and clip saving (:590-621) are
+the product's control plane and stay with the caller."""
+from typing import Dict, Hashable, List, NamedTuple, Optional
+
+import numpy as np
+import torch
+
+from .ocsort_tracker import ocsort
+from .ocsort_tracker.STrack import STrack
+
+
+class CameraResult(NamedTuple):
+    rows: np.ndarray            # (300,6) float32 detector output in this camera's frame coordinates
+    targets: List[STrack]       # tracker.update(rows, thresh), unfiltered (clearcam.py:585)
+    preds: np.ndarray           # (k,7) x1,y1,x2,y2,score,class,track_id of targets seen for more than one frame
+
+
+class _Camera:
+    def __init__(self, thresh, classes, max_age):
+        self.thresh, self.classes = thresh, classes
+        self.tracker = ocsort.OCSort(max_age=max_age)          # clearcam.py:239
+
+
+class CameraBatch:
+    def __init__(self, model, max_age: int = 100):
+        """model: a clearcam_b200 YOLOv9 (anything with detect_batch(frames[B,H,W,3]) -> (B,300,6))."""
+        self.model, self.max_age = model, max_age
+        self.cams: Dict[Hashable, _Camera] = {}
+        self._stage: Dict[tuple, tuple] = {}                   # (H,W,dtype,n) -> (pinned frames, pinned rows)
+        self._pin = torch.cuda.is_available()
+
+    # -- camera set (clearcam.py:207-240 init_cam; settings threshold :584, class filter :586)
+    def add_camera(self, name, thresh: float = 0.5, classes=None):
+        self.cams[name] = _Camera(thresh or 0.5, None if classes is None else {int(c) for c in classes}, self.max_age)
+
+    def remove_camera(self, name):
+        self.cams.pop(name, None)
+
+    def reset_tracker(self, name):
+        self.cams[name].tracker = ocsort.OCSort(max_age=self.max_age)
+
+    # -- one pass over every camera that has a new frame
+    @staticmethod
+    def group_by_shape(frames: Dict[Hashable, np.ndarray]) -> Dict[tuple, List[Hashable]]:
+        groups: Dict[tuple, List[Hashable]] = {}
+        for name, f in frames.items():
+            if f is None:
+                continue
+            if f.ndim != 3 or f.shape[2] != 3 or f.dtype not in (np.uint8, np.float32):
+                raise ValueError(f"camera {name!r}: frame must be HWC BGR uint8 or float32, got {f.dtype} {f.shape}")
+            groups.setdefault((f.shape[0], f.shape[1], f.dtype.str), []).append(name)
+        return groups
+
+    def _buffers(self, key, n):
+        k = key + (n,)
+        if k not in self._stage:
+            H, W, dt = key
+            tdt = torch.uint8 if np.dtype(dt) == np.uint8 else torch.float32
+            self._stage[k] = (torch.empty((n, H, W, 3), dtype=tdt, pin_memory=self._pin),
+                              torch.empty((n, 300, 6), dtype=torch.float32, pin_memory=self._pin))
+        return self._stage[k]
+
+    def detect(self, frames: Dict[Hashable, np.ndarray]) -> Dict[Hashable, np.ndarray]:
+        """Detector only: {camera: HWC frame} -> {camera: (300,6) rows}.  One batched call per distinct frame shape."""
+        pending = []
+        for key, names in self.group_by_shape(frames).items():
+            stage, rows = self._buffers(key, len(names))
+            view = stage.numpy()
+            for i, name in enumerate(names):
+                np.copyto(view[i], frames[name])
+            dev = stage.to("cuda", non_blocking=True) if self._pin else stage
+            out = self.model.detect_batch(dev)
+            rows.copy_(out, non_blocking=True)
+            pending.append((names, rows))
+        if self._pin:
+            torch.cuda.current_stream().synchronize()
+        return {name: rows[i].numpy().copy() for names, rows in pending for i, name in enumerate(names)}
+
+    def step(self, frames: Dict[Hashable, np.ndarray]) -> Dict[Hashable, CameraResult]:
+        for name in frames:
+            if name not in self.cams:
+                self.add_camera(name)
+        det = self.detect(frames)
+        names = list(det)
+        if not names:
+            return {}
+        targets = ocsort.update_many([self.cams[n].tracker for n in names], np.stack([det[n] for n in names]),
+                                     [self.cams[n].thresh for n in names])
+        res = {}
+        for name, tg in zip(names, targets):
+            cam = self.cams[name]
+            if cam.classes is not None:
+                tg = [t for t in tg if int(t.class_id) in cam.classes]                       # clearcam.py:586
+            keep = [t for t in tg if t.tracklet_len >= 1]                                     # clearcam.py:589
+            preds = np.array([[t.tlwh[0], t.tlwh[1], t.tlwh[0] + t.tlwh[2], t.tlwh[1] + t.tlwh[3], t.score, t.class_id, t.track_id]
+                              for t in keep], np.float64).reshape(-1, 7)
+            res[name] = CameraResult(det[name], tg, preds)
+        return res

@@ -187,3 +187,31 @@ def test_real_yolov9t_weights_real_frame():
     assert n_want >= 30 and abs(n_want - n_got) <= 3
     frac, _ = _match(want, got)
     assert frac >= 0.85, f"matched {frac}"
+
+
+def test_multi_camera_batch_matches_single_frame_calls():
+    """CameraBatch.step (one detect_batch per frame shape, then all trackers) gives every camera what the reference's
+    per-camera loop gives it: model(frame).numpy() -> tracker.update (clearcam.py:582-585)."""
+    from clearcam_b200.cameras import CameraBatch
+    from clearcam_b200.ocsort_tracker import ocsort
+    fr, x, P = _setup("t", 320, 3, 240, 320, seed=2)
+    wide = o.synthetic_frames(2, 180, 320, seed=7)
+    m = YOLOv9("t", 320, weights=P)
+    cb = CameraBatch(m)
+    solo = {}
+    for t in range(3):
+        frames = {f"a{i}": np.roll(fr[i].numpy(), 4 * t, axis=1) for i in range(3)}
+        frames.update({f"w{i}": np.roll(wide[i].numpy(), 4 * t, axis=1) for i in range(2)})
+        res = cb.step(frames)
+        assert set(res) == set(frames)
+        for name, f in frames.items():
+            single = m(f).numpy()
+            got = res[name].rows
+            live = single[:, 4] > 0
+            assert (got[:, 4] > 0).sum() == live.sum()
+            # the batched plan may tile a layer differently from the B=1 plan; boxes agree to well inside a pixel
+            assert np.abs(got[live][:, :4] - single[live][:, :4]).max() < 0.5 and np.abs(got[live][:, 4] - single[live][:, 4]).max() < 0.01
+            assert (got[live][:, 5] == single[live][:, 5]).all()
+            trk = solo.setdefault(name, ocsort.OCSort(max_age=100))
+            exp = trk.update(got, 0.5)
+            assert [int(t_.track_id) for t_ in exp] == [int(t_.track_id) for t_ in res[name].targets]
