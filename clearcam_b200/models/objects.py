@@ -225,6 +225,47 @@ class ObjectFinder:
         img = cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
         return [self.preprocess(img)]
 
+    # ---- objects cut out of frames that are already on the device
+    @staticmethod
+    def crop_rect(box_xyxy, W: int, H: int, min_side: int = 100):
+        """`save_object`'s rectangle (clearcam.py:381-395): the box grown to twice its size about its centre in integer
+        arithmetic, clamped to the frame; None when a side is under 100 px ("too small")."""
+        x1, y1, x2, y2 = (int(v) for v in box_xyxy)
+        cx, cy = (x1 + x2) // 2, (y1 + y2) // 2
+        hw, hh = (x2 - x1) // 2 * 2, (y2 - y1) // 2 * 2
+        nx1, nx2 = max(0, min(cx - hw, W)), max(0, min(cx + hw, W))
+        ny1, ny2 = max(0, min(cy - hh, H)), max(0, min(cy + hh, H))
+        if (ny2 - ny1) < min_side or (nx2 - nx1) < min_side:
+            return None
+        return nx1, ny1, nx2, ny2
+
+    def preprocess_device(self, frames, rects, bgr: bool = True, size: Optional[int] = None):
+        """frames: uint8 [n,H,W,3] or [H,W,3] (host or device; BGR as the cameras deliver them), rects: K rows of
+        (frame, x1, y1, x2, y2) or (x1, y1, x2, y2) -> DeviceResult (K,3,S,S) float32, bit-identical to
+        `preprocess(cv2.cvtColor(frame[y1:y2, x1:x2], BGR2RGB))` with OpenCV's own bicubic — without leaving the GPU."""
+        t = frames.tensor if isinstance(frames, DeviceResult) else frames
+        if not isinstance(t, torch.Tensor):
+            t = torch.from_numpy(np.ascontiguousarray(t))
+        if t.dim() == 3:
+            t = t.unsqueeze(0)
+        if t.dtype != torch.uint8 or t.dim() != 4 or t.shape[-1] != 3:
+            raise ValueError("frames must be uint8 [n,H,W,3]")
+        t = t.to("cuda", non_blocking=True).contiguous()
+        r = np.asarray(rects, np.int32).reshape(-1, np.shape(rects)[-1] if len(rects) else 5)
+        if r.shape[1] == 4:
+            r = np.concatenate([np.zeros((len(r), 1), np.int32), r], 1)
+        r = np.ascontiguousarray(r, np.int32)
+        s = size or (self.model.image_size if self.model is not None else 224)
+        out = torch.empty(len(r), 3, s, s, device="cuda", dtype=torch.float32)
+        check(lib().cc_clip_preprocess(ptr(t), t.shape[0], t.shape[1], t.shape[2], r.ctypes.data, len(r), s, int(bgr), ptr(out),
+                                       stream_ptr(None)), "cc_clip_preprocess")
+        return DeviceResult(out)
+
+    def embed_crops(self, frames, rects, bgr: bool = True):
+        """Detector frame -> embeddings of its objects in one device pass: crop + preprocess + `precompute_embedding`
+        (the reference goes through cv2.imwrite / cv2.imread and the host, clearcam.py:398, 274-276)."""
+        return self.model.precompute_embedding(self.preprocess_device(frames, rects, bgr))
+
     def _device_index(self):
         keys = [k for k, v in self.image_embeddings.items() if v is not None]
         if self._index is None or self._index[0] != keys:

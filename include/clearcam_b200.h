@@ -124,6 +124,14 @@ int cc_clip_profile(cc_clip* h, int text, const void* d_in, int B, float* d_out,
 /* ObjectFinder.search inner loop (models/objects.py:365-376): d_scores[q*N + n] = <d_index[n,:], d_q[q,:]>, fp32. */
 int cc_search_scores(const float* d_index, int N, int D, const float* d_q, int Q, float* d_scores, void* stream);
 
+/* Crop + ObjectFinder.preprocess on the device, for objects cut out of frames already resident for the detector:
+ * frame[y1:y2, x1:x2] (clearcam.py:396) -> BGR->RGB when bgr != 0 (models/objects.py:249) -> cv2.resize((size,size),
+ * INTER_CUBIC) -> /255 -> (x-0.5)/0.5 -> CHW (models/objects.py:237-242).  d_frames: device uint8 [n_frames,H,W,3];
+ * rects: HOST int32 [K,5] = frame, x1, y1, x2, y2 (validated, passed as kernel arguments: no copy, no sync);
+ * d_out: device float32 [K,3,size,size] — the tensor cc_clip_encode_image takes. */
+int cc_clip_preprocess(const uint8_t* d_frames, int n_frames, int H, int W, const int32_t* rects, int K, int size, int bgr,
+                       float* d_out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Tracker that consumes the detector rows (host code, no GPU): ocsort_tracker/ocsort.py:163-308 `OCSort`, with
  * association.py and kalmanfilter.py.  One handle per camera (clearcam.py:239 `ocsort.OCSort(max_age=100)`).

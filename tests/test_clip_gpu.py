@@ -82,3 +82,45 @@ def test_search_matches_reference_semantics(tmp_path):
     assert [p for p, _ in res] == [p for p, _ in want]
     assert np.allclose([s for _, s in res], [s for _, s in want], atol=1e-5)
     assert all("/cameras/cam1/" in p for p, _ in f.search(top_k=50, text_embedding=q[0].numpy(), cam_name="cam1"))
+
+
+# ------------------------------------------------------------------------------------------------ crop -> CLIP input
+def test_device_crop_preprocess_bit_exact():
+    """cc_clip_preprocess == crop + cvtColor + ObjectFinder.preprocess with OpenCV's bicubic (oracle pinned to cv2)."""
+    from pathlib import Path
+    from oracle import clip_preprocess as cp
+    g = np.load(Path(__file__).parent / "golden" / "clip_preprocess.npz")
+    of = ObjectFinder()
+    got = of.preprocess_device(g["frame"], g["rects"]).tensor.cpu().numpy()
+    want = np.stack([np.transpose((r.astype(np.float32) / 255.0 - 0.5) / 0.5, (2, 0, 1)) for r in g["resized"]])
+    np.testing.assert_array_equal(got, want)                                 # cv2's own output, committed
+    # several frames, > 64 rects (two launches), up- and down-scaling, 1-pixel-wide and full-frame crops, RGB input
+    rng = np.random.default_rng(5)
+    frames = rng.integers(0, 256, (3, 270, 480, 3), dtype=np.uint8)
+    rects = [(0, 0, 0, 480, 270), (1, 5, 7, 6, 200), (2, 100, 100, 324, 324), (2, 0, 269, 480, 270)]
+    for _ in range(70):
+        x1, y1 = int(rng.integers(0, 470)), int(rng.integers(0, 260))
+        rects.append((int(rng.integers(0, 3)), x1, y1, int(rng.integers(x1 + 1, 481)), int(rng.integers(y1 + 1, 271))))
+    for bgr in (True, False):
+        got = of.preprocess_device(torch.from_numpy(frames).cuda(), rects, bgr=bgr).tensor.cpu().numpy()
+        for k, (f, x1, y1, x2, y2) in enumerate(rects):
+            crop = frames[f, y1:y2, x1:x2, ::-1] if bgr else frames[f, y1:y2, x1:x2]
+            np.testing.assert_array_equal(got[k], cp.normalize(cp.resize_cubic_u8(np.ascontiguousarray(crop), 224, 224)), err_msg=str(rects[k]))
+    got = of.preprocess_device(frames[0], [(10, 10, 200, 150)], size=37).tensor.cpu().numpy()      # tail columns: integer form
+    np.testing.assert_array_equal(got[0], cp.normalize(cp.resize_cubic_u8(np.ascontiguousarray(frames[0, 10:150, 10:200, ::-1]), 37, 37)))
+    with pytest.raises(Exception):
+        of.preprocess_device(frames, [(0, 10, 10, 500, 100)])               # outside the frame: refused, not clamped
+
+
+def test_embed_crops_end_to_end():
+    from pathlib import Path
+    from oracle import clip_preprocess as cp
+    g = np.load(Path(__file__).parent / "golden" / "clip_preprocess.npz")
+    cfg = oc.CONFIGS["ViT-B/32"]
+    P = oc.synthetic_weights(cfg, seed=3)
+    of = ObjectFinder()
+    of.model = OpenCLIP(weights=P, arch="ViT-B/32")
+    got = of.embed_crops(g["frame"], g["rects"]).tensor.cpu()
+    with torch.no_grad():
+        want = oc.encode_image(cfg, P, torch.from_numpy(cp.preprocess_crops(g["frame"], g["rects"])))
+    _check(got, want)
