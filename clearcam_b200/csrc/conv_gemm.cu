@@ -61,6 +61,24 @@ __device__ __forceinline__ float act_apply(float x) {
   return x;
 }
 
+// x / d for x < 2^31 with the host-computed (mul, shift) of fast_div(): (umulhi(mul, x) + x) >> shift
+__device__ __forceinline__ int fdiv(int x, const uint32_t fd[2]) {
+  return static_cast<int>((__umulhi(fd[0], static_cast<uint32_t>(x)) + static_cast<uint32_t>(x)) >> fd[1]);
+}
+// tile -> n block, tile origin
+struct TileXY { int nb, w0, h0, n0; };
+__device__ __forceinline__ TileXY tile_origin(const GemmParams& p, int tile, int lw) {
+  TileXY t;
+  const int m = fdiv(tile, p.fd_nb);
+  t.nb = tile - m * p.n_blocks;
+  const int mh = fdiv(m, p.fd_tw);                 // m / tiles_w
+  t.w0 = (m - mh * p.tiles_w) << lw;
+  const int n = fdiv(m, p.fd_twh);                 // m / (tiles_w * tiles_h)
+  t.h0 = (mh - n * p.tiles_h) << p.lTH;
+  t.n0 = n << p.lTN;
+  return t;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -207,7 +225,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], kEpiThreads);
+      mbar_init(&tempty_bar[i], p.epi_threads);
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&afull_bar[i], 1);
@@ -236,7 +254,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   pdl_trigger();
 
   const int num_kb = p.num_taps * p.chunks_per_tap;
-  const int tiles_wh = p.tiles_w * p.tiles_h;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -253,11 +270,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         uint32_t pa = 0;
         const int cin = p.chunks_per_tap * p.BK;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-          const int nb = tile % p.n_blocks;
-          const int m = tile / p.n_blocks;
-          const int w0 = (m % p.tiles_w) << 3;
-          const int h0 = ((m / p.tiles_w) % p.tiles_h) << p.lTH;
-          const int n0 = (m / tiles_wh) << p.lTN;
+          const TileXY tx = tile_origin(p, tile, 3);
+          const int nb = tx.nb, w0 = tx.w0, h0 = tx.h0, n0 = tx.n0;
           for (int ch = 0; ch < p.chunks_per_tap; ++ch) {
             mbar_wait(&aempty_bar[sa], pa ^ 1);
             mbar_arrive_expect_tx(&afull_bar[sa], p.halo_bytes);
@@ -274,11 +288,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         }
       } else
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int nb = tile % p.n_blocks;
-        const int m = tile / p.n_blocks;
-        const int w0 = (m % p.tiles_w) << p.lTW;
-        const int h0 = ((m / p.tiles_w) % p.tiles_h) << p.lTH;
-        const int n0 = (m / tiles_wh) << p.lTN;
+        const TileXY tx = tile_origin(p, tile, p.lTW);
+        const int nb = tx.nb, w0 = tx.w0, h0 = tx.h0, n0 = tx.n0;
         int kb = 0;
         for (int t = 0; t < p.num_taps; ++t) {
           const int c_base = p.tap[t][0];
@@ -301,7 +312,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     if (p.BK == 64) mma_issuer<4>(p, sA, sB, row_bytes, a_bytes, b_bytes, S, num_kb, full_bar, empty_bar, tfull_bar, tempty_bar, afull_bar, aempty_bar, bres_bar, tmem_base);
     else if (p.BK == 32) mma_issuer<2>(p, sA, sB, row_bytes, a_bytes, b_bytes, S, num_kb, full_bar, empty_bar, tfull_bar, tempty_bar, afull_bar, aempty_bar, bres_bar, tmem_base);
     else mma_issuer<1>(p, sA, sB, row_bytes, a_bytes, b_bytes, S, num_kb, full_bar, empty_bar, tfull_bar, tempty_bar, afull_bar, aempty_bar, bres_bar, tmem_base);
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 4 + (p.epi_threads >> 5)) {
+    // (narrow tiles: warps without a 16-column chunk to convert sit the kernel out instead of paying the per-tile
+    //  bookkeeping and barriers)
     // ===================== epilogue: 8 warps; warps q and q+4 share TMEM lane quarter q and split the
     // 16-column chunks between them (even / odd); thread == output row in the register phase ============
     const int ew = warp & 3;                   // TMEM lane quarter this warp may access
@@ -313,6 +326,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     uint32_t acc_phase = 0;
     uint32_t pass_ctr = 0;   // staging passes issued so far (TMA-store double buffering)
     const int passes_per_tile = (p.BN + CH - 1) / CH;
+    const int cstep = (p.epi_threads >> 7) * 16;   // column stride between the chunks one warp converts
+    // TMA-store staging: rows of 128 B (SWIZZLE_128B: 16-B chunk j of row r at slot j ^ (r & 7)) or, for tiles whose
+    // pass is an odd multiple of 64 B, rows of 64 B (SWIZZLE_64B: slot j ^ ((r >> 1) & 3)); sub-tiles of 128 rows follow
+    // each other
+    const int lrow = p.stg_lrow, srow = 1 << lrow;
+    const uint32_t swz = lrow == 7 ? (row & 7) : ((row >> 1) & 3);
     // residual prefetch (in-place residual through tmC): the TMA load of the residual sub-tiles of staging pass `k`
     // lands in the buffer the pass will overwrite with its result; issued one pass ahead by thread et == 0
     auto issue_res = [&](uint32_t k) {
@@ -321,26 +340,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       if (tile_k >= p.num_tiles) return;
       const int cc0k = (static_cast<int>(k) - t_idx * passes_per_tile) * CH;
       const int chnk = (p.BN - cc0k) < CH ? (p.BN - cc0k) : CH;
-      const int nbk = tile_k % p.n_blocks, mk = tile_k / p.n_blocks;
-      const int w0k = (mk % p.tiles_w) << p.lTW, h0k = ((mk / p.tiles_w) % p.tiles_h) << p.lTH, n0k = (mk / tiles_wh) << p.lTN;
+      const TileXY tk = tile_origin(p, tile_k, p.lTW);
+      const int nbk = tk.nb, w0k = tk.w0, h0k = tk.h0, n0k = tk.n0;
       const int b = (p.stg_bufs == 2) ? (k & 1) : 0;
       uint8_t* dstb = sStage + b * stg_bytes;
-      const int nsub = (chnk * es) >> 7;
-      mbar_arrive_expect_tx(&res_bar[b], nsub * (kTileM * 128));
+      const int nsub = (chnk * es) >> lrow;
+      mbar_arrive_expect_tx(&res_bar[b], nsub * (kTileM << lrow));
       for (int j = 0; j < nsub; ++j) {
-        const int cc = nbk * p.BN + cc0k + j * (128 / es);
-        if (p.halo) tma_load_5d(dstb + j * (kTileM * 128), &p.tmC, &res_bar[b], cc, w0k, n0k, h0k, 0);
-        else tma_load_5d(dstb + j * (kTileM * 128), &p.tmC, &res_bar[b], cc, w0k, h0k, n0k, 0);
+        const int cc = nbk * p.BN + cc0k + j * (srow / es);
+        if (p.halo) tma_load_5d(dstb + j * (kTileM << lrow), &p.tmC, &res_bar[b], cc, w0k, n0k, h0k, 0);
+        else tma_load_5d(dstb + j * (kTileM << lrow), &p.tmC, &res_bar[b], cc, w0k, h0k, n0k, 0);
       }
     };
     pdl_wait();   // residual reads below depend on the previous kernel's output
     if (p.res_tma == 1 && et == 0) issue_res(0);
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int nb = tile % p.n_blocks;
-      const int m = tile / p.n_blocks;
-      const int w0 = (m % p.tiles_w) << p.lTW;
-      const int h0 = ((m / p.tiles_w) % p.tiles_h) << p.lTH;
-      const int n0 = (m / tiles_wh) << p.lTN;
+      const TileXY tx = tile_origin(p, tile, p.lTW);
+      const int nb = tx.nb, w0 = tx.w0, h0 = tx.h0, n0 = tx.n0;
 
       // this thread's pixel (register phase: residual read)
       int pw, ph, pn;
@@ -368,9 +384,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           const uint32_t par = (p.stg_bufs == 2) ? ((pass_ctr >> 1) & 1) : (pass_ctr & 1);
           mbar_wait(&res_bar[b], par);
         } else {
-          named_bar_sync(1, kEpiThreads);                        // staging buffer free
+          named_bar_sync(1, p.epi_threads);                        // staging buffer free
         }
-        for (int c = half * 16; c < chn; c += 16 * kColGroups) {
+        for (int c = half * 16; c < chn; c += cstep) {
           uint32_t v[16];
           tmem_ld16(t_row + cc0 + c, v);
           const int gcol = nb * p.BN + cc0 + c;  // global output channel of v[0]
@@ -388,18 +404,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             // nothing to read: the TMA reduce-add store adds the residual in place
           } else if (p.res_tma == 1) {
             const uint32_t boff = c * es;
-            const uint8_t* sub = sbuf + (boff >> 7) * (kTileM * 128) + row * 128;
-            const uint32_t ch0 = (boff & 127) >> 4;
+            const uint8_t* sub = sbuf + (boff >> lrow) * (kTileM << lrow) + (row << lrow);
+            const uint32_t ch0 = (boff & (srow - 1)) >> 4;
             if (F32) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const float4 r = *reinterpret_cast<const float4*>(sub + (((ch0 + j) ^ (row & 7)) << 4));
+                const float4 r = *reinterpret_cast<const float4*>(sub + (((ch0 + j) ^ swz) << 4));
                 f[4 * j + 0] += r.x; f[4 * j + 1] += r.y; f[4 * j + 2] += r.z; f[4 * j + 3] += r.w;
               }
             } else {
 #pragma unroll
               for (int j = 0; j < 2; ++j) {
-                const uint4 r = *reinterpret_cast<const uint4*>(sub + (((ch0 + j) ^ (row & 7)) << 4));
+                const uint4 r = *reinterpret_cast<const uint4*>(sub + (((ch0 + j) ^ swz) << 4));
                 const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -434,20 +450,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             }
           }
           if (p.tma_store) {
-            // 128-B rows, 16-B chunk j of row r at slot j ^ (r & 7) (the layout a SWIZZLE_128B TMA store reads);
-            // sub-tiles of 128 B x 128 rows follow each other
             const uint32_t boff = c * es;                       // byte offset of this 16-column group in the pass row
-            uint8_t* sub = sbuf + (boff >> 7) * (kTileM * 128) + row * 128;
-            const uint32_t ch0 = (boff & 127) >> 4;
+            uint8_t* sub = sbuf + (boff >> lrow) * (kTileM << lrow) + (row << lrow);
+            const uint32_t ch0 = (boff & (srow - 1)) >> 4;
             if (F32) {
 #pragma unroll
               for (int j = 0; j < 4; ++j)
-                *reinterpret_cast<float4*>(sub + (((ch0 + j) ^ (row & 7)) << 4)) =
+                *reinterpret_cast<float4*>(sub + (((ch0 + j) ^ swz) << 4)) =
                     make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
             } else {
 #pragma unroll
               for (int j = 0; j < 2; ++j)
-                *reinterpret_cast<uint4*>(sub + (((ch0 + j) ^ (row & 7)) << 4)) =
+                *reinterpret_cast<uint4*>(sub + (((ch0 + j) ^ swz) << 4)) =
                     make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
                                pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
             }
@@ -473,17 +487,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         }
         if (p.tma_store) {
           fence_proxy_async_smem();        // generic-proxy smem writes -> visible to the TMA (async proxy)
-          named_bar_sync(1, kEpiThreads);  // staging filled
+          named_bar_sync(1, p.epi_threads);  // staging filled
           if (et == 0) {
-            const int nsub = (chn * es) >> 7;
+            const int nsub = (chn * es) >> lrow;
             const int col0 = nb * p.BN + cc0;
             for (int j = 0; j < nsub; ++j) {
-              const int cc = col0 + j * (128 / es);
+              const int cc = col0 + j * (srow / es);
               if (p.res_tma == 2) {   // out += tile (fp32 in-place residual, added at the L2)
-                if (p.halo) tma_reduce_add_5d(&p.tmC, sbuf + j * (kTileM * 128), cc, w0, n0, h0, 0);
-                else tma_reduce_add_5d(&p.tmC, sbuf + j * (kTileM * 128), cc, w0, h0, n0, 0);
-              } else if (p.halo) tma_store_5d(&p.tmC, sbuf + j * (kTileM * 128), cc, w0, n0, h0, 0);
-              else tma_store_5d(&p.tmC, sbuf + j * (kTileM * 128), cc, w0, h0, n0, 0);
+                if (p.halo) tma_reduce_add_5d(&p.tmC, sbuf + j * (kTileM << lrow), cc, w0, n0, h0, 0);
+                else tma_reduce_add_5d(&p.tmC, sbuf + j * (kTileM << lrow), cc, w0, h0, n0, 0);
+              } else if (p.halo) tma_store_5d(&p.tmC, sbuf + j * (kTileM << lrow), cc, w0, n0, h0, 0);
+              else tma_store_5d(&p.tmC, sbuf + j * (kTileM << lrow), cc, w0, h0, n0, 0);
             }
             tma_store_commit();
             if (p.res_tma == 1) {
@@ -495,12 +509,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           ++pass_ctr;
           continue;
         }
-        named_bar_sync(1, kEpiThreads);  // staging filled
+        named_bar_sync(1, p.epi_threads);  // staging filled
         // coalesced copy-out, division free: a group of `gsz` (power of two >= chunks per row) lanes owns one row
         const int cpr = (chn * es) >> 4;  // 16-B chunks per row (2..16)
         const int lg = cpr > 8 ? 4 : (cpr > 4 ? 3 : (cpr > 2 ? 2 : 1));
         const int chk = et & ((1 << lg) - 1);
-        const int rstep = kEpiThreads >> lg;
+        const int rstep = p.epi_threads >> lg;
         if (chk < cpr) {
           uint8_t* gbase = reinterpret_cast<uint8_t*>(p.out) + static_cast<size_t>(p.out_co + nb * p.BN + cc0) * es + chk * 16;
           for (int r = et >> lg; r < kTileM; r += rstep) {
@@ -703,7 +717,13 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
   // ---- smem budget -> pipeline depth
   const int CH = d.out_f32 ? (BN < 64 ? BN : 64) : (BN < 128 ? BN : 128);
   static const int tmas_env = getenv("CC_TMASTORE") ? atoi(getenv("CC_TMASTORE")) : 1;
+  static const int tmas64_env = getenv("CC_TMASTORE64") ? atoi(getenv("CC_TMASTORE64")) : 1;
+  p.stg_lrow = 7;
   p.tma_store = (tmas_env && (BN * es) % 128 == 0) ? 1 : 0;
+  if (!p.tma_store && tmas_env && tmas64_env && (BN * es) % 64 == 0) {   // narrow tiles (BN = 32 bf16, 16 fp32, ...): 64-B rows
+    p.tma_store = 1;
+    p.stg_lrow = 6;
+  }
   p.stg_bufs = 1;
   if (p.tma_store) {
     // double-buffer the staging when the pipeline still gets >= 4 stages (per-tap mode) / 3 B stages (halo mode)
@@ -720,14 +740,15 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
     if (p.halo) {
       dims[0] = d.Cout; dims[1] = Wout; dims[2] = d.N; dims[3] = Hout; dims[4] = 1;
       strides[0] = px; strides[1] = img; strides[2] = px * Wout; strides[3] = img * d.N;
-      box[0] = 128 / es; box[1] = 8; box[2] = TN; box[3] = TH; box[4] = 1;
+      box[0] = (1 << p.stg_lrow) / es; box[1] = 8; box[2] = TN; box[3] = TH; box[4] = 1;
     } else {
       dims[0] = d.Cout; dims[1] = Wout; dims[2] = Hout; dims[3] = d.N; dims[4] = 1;
       strides[0] = px; strides[1] = px * Wout; strides[2] = img; strides[3] = img * d.N;
-      box[0] = 128 / es; box[1] = TW; box[2] = TH; box[3] = TN; box[4] = 1;
+      box[0] = (1 << p.stg_lrow) / es; box[1] = TW; box[2] = TH; box[3] = TN; box[4] = 1;
     }
     CUresult r = enc(&p.tmC, d.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims,
-                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     p.stg_lrow == 7 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                      CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     CC_REQUIRE(r == CUDA_SUCCESS, "conv_gemm: cuTensorMapEncodeTiled(C) failed: %d", int(r));
   }
@@ -740,6 +761,22 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
   const int fixed = 1024 /*align slack*/ + staging + d.Cout * 4 /*bias*/ + 320 /*barriers*/;
   int S;
   static const int bres_env = getenv("CC_BRES") ? atoi(getenv("CC_BRES")) : 1;
+  static const int epidyn_env = getenv("CC_EPI_DYN") ? atoi(getenv("CC_EPI_DYN")) : 1;
+  {
+    auto fast_div = [](uint32_t d, uint32_t fd[2]) {      // q = (umulhi(mul, x) + x) >> shift for x < 2^31
+      uint32_t l = 0;
+      while ((1ull << l) < d) ++l;
+      fd[0] = static_cast<uint32_t>(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+      fd[1] = l;
+    };
+    fast_div(p.n_blocks, p.fd_nb);
+    fast_div(p.tiles_w, p.fd_tw);
+    fast_div(p.tiles_h, p.fd_th);
+    fast_div(p.tiles_w * p.tiles_h, p.fd_twh);
+    const int CHh = d.out_f32 ? (BN < 64 ? BN : 64) : (BN < 128 ? BN : 128);
+    const int groups = CHh / 16 < kColGroups ? CHh / 16 : kColGroups;
+    p.epi_threads = epidyn_env ? 128 * groups : kEpiThreads;
+  }
   static const int hst_env = getenv("CC_HALO_STAGES") ? atoi(getenv("CC_HALO_STAGES")) : 0;
   const int bres_bytes = BN * p.BK * 2 * p.num_taps * p.chunks_per_tap;
   p.b_res = (bres_env && p.n_blocks == 1 && bres_bytes <= 80 * 1024) ? 1 : 0;

@@ -25,6 +25,11 @@ CASES = [
     (2, 40, 40, 256, 512, 1, 1, 1, False, False, 256, 0, 512, 0, 256),
     (4, 48, 80, 128, 128, 3, 2, 1, False, False, 256, 128, 128, 0, 0),
     (32, 40, 40, 256, 256, 3, 1, 1, False, False, 256, 0, 256, 0, 0),
+    # narrow tiles: the TMA-store staging uses 64-byte rows (SWIZZLE_64B) and only part of the epilogue warps
+    (2, 40, 40, 32, 32, 3, 1, 1, True, False, 64, 32, 64, 0, 0),
+    (2, 20, 20, 64, 16, 1, 1, 0, False, True, 64, 0, 16, 0, 0),
+    (2, 20, 20, 64, 96, 3, 1, 1, False, False, 64, 0, 96, 0, 0),
+    (3, 33, 21, 48, 16, 3, 1, 1, False, False, 48, 0, 48, 16, 0),
 ]
 
 
@@ -70,3 +75,26 @@ def test_conv_matches_torch(case, impl):
         mask = torch.ones(out_cs, dtype=torch.bool, device=dev)
         mask[out_co:out_co + Cout] = False
         assert (obuf[..., mask] == -7.0).all()
+
+
+@pytest.mark.parametrize("Cout,out_f32,k", [(32, False, 3), (64, False, 3), (128, False, 1), (16, True, 1), (64, True, 3), (96, False, 1)])
+def test_conv_in_place_residual(Cout, out_f32, k):
+    """out = act(conv(x)) + out, the RepNBottleneck / transformer residual form: the residual tile is prefetched into
+    the staging buffer by TMA (bf16) or added by a TMA reduce-add store (fp32) — through the same tensor map as the store,
+    in both staging row widths."""
+    g = torch.Generator(device="cuda").manual_seed(77 + Cout)
+    N, H, W, Cin = 3, 24, 40, 64
+    x = torch.randn(N, H, W, Cin, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(Cout, k, k, Cin, device="cuda", generator=g) * (2.0 / (k * k * Cin)) ** 0.5).to(torch.bfloat16)
+    b = torch.randn(Cout, device="cuda", generator=g) * 0.1
+    odt = torch.float32 if out_f32 else torch.bfloat16
+    out_cs, out_co = 2 * Cout, Cout
+    obuf = torch.randn(N, H, W, out_cs, device="cuda", generator=g).to(odt)
+    before = obuf.clone()
+    ops.conv2d(x, 0, Cin, w, b, k, 1, obuf, out_co, Cout, act=1, res=obuf, res_co=out_co, impl=1)
+    torch.cuda.synchronize()
+    ref = _ref(x.float(), w.float(), b, k, 1, 1, before[..., out_co:].float())
+    got = obuf[..., out_co:].float()
+    err = ((got - ref).abs() / ref.abs().clamp(min=1.0)).max().item()
+    assert err < (2e-3 if out_f32 else 2e-2), err
+    assert torch.equal(obuf[..., :out_co], before[..., :out_co])

@@ -16,6 +16,7 @@ shapes = [  # N,H,W,Cin,Cout,k,s
 sel = [int(a) for a in sys.argv[2:]] or range(len(shapes))
 for si in sel:
     N, H, W, Cin, Cout, k, s = shapes[si]
+    N = int(os.environ.get("ONE_CONV_N", N))
     x = torch.randn(N, H, W, Cin, device="cuda").to(torch.bfloat16)
     w = (torch.randn(Cout, k, k, Cin, device="cuda") * 0.05).to(torch.bfloat16)
     b = torch.randn(Cout, device="cuda")
