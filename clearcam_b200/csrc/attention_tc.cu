@@ -64,9 +64,9 @@ __global__ void __launch_bounds__(160) attention_tc_kernel(const __grid_constant
   uint64_t* bar_v = bars + 1;    // V^T landed
   uint64_t* bar_q = bars + 2;    // Q block landed            (phase per q-block)
   uint64_t* bar_s = bars + 3;    // S = QK^T complete
-  uint64_t* bar_p = bars + 4;    // P written (128 arrivals)
+  uint64_t* bar_p = bars + 4;    // P written (4 arrivals: one per softmax warp)
   uint64_t* bar_o = bars + 5;    // O = PV complete
-  uint64_t* bar_oe = bars + 6;   // O read back (128 arrivals)
+  uint64_t* bar_oe = bars + 6;   // O read back (4 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
 
   const int bh = blockIdx.x, b = bh / p.H, h = bh % p.H;
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(160) attention_tc_kernel(const __grid_constant
       tma_prefetch_desc(&p.tmQK);
       tma_prefetch_desc(&p.tmVt);
       mbar_init(bar_k, 1); mbar_init(bar_v, 1); mbar_init(bar_q, 1); mbar_init(bar_s, 1);
-      mbar_init(bar_p, 128); mbar_init(bar_o, 1); mbar_init(bar_oe, 128);
+      mbar_init(bar_p, 4); mbar_init(bar_o, 1); mbar_init(bar_oe, 4);   // one arrival per softmax warp
       fence_mbar_init();
     }
     __syncwarp();
@@ -202,7 +202,8 @@ __global__ void __launch_bounds__(160) attention_tc_kernel(const __grid_constant
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(bar_p);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p);
       // ---- O -> ctx
       mbar_wait(bar_o, ph);
       tc_fence_after();
@@ -228,7 +229,8 @@ __global__ void __launch_bounds__(160) attention_tc_kernel(const __grid_constant
         }
       }
       tc_fence_before();
-      mbar_arrive(bar_oe);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_oe);
     }
   }
   tc_fence_before();

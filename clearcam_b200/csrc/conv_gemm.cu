@@ -84,11 +84,22 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// ---- MMA issuer role (warp 1), templated on the number of UMMA_K=16 steps per k-block so the issue sequence is
-// straight-line code.  The WHOLE warp runs the loop with warp-uniform values and one elected lane issues: descriptors
-// and TMEM addresses then live in uniform registers (a single active lane made ptxas wrap every tcgen05.mma in an
-// ELECT/R2UR.BROADCAST loop: ~100 SASS instructions per k-block, more than its 256 tensor cycles at BN=128).
+// ---- MMA issuer role (warp 1), templated on the number of UMMA_K=16 steps per k-block and on resident weights so the
+// issue sequence is straight-line code.  The WHOLE warp runs the loop with warp-uniform values and one elected lane
+// issues: descriptors and TMEM addresses then live in uniform registers (a single active lane made ptxas wrap every
+// tcgen05.mma in an ELECT/R2UR.BROADCAST loop: ~100 SASS instructions per k-block).  Every elect block costs the warp
+// ~60 dependent instructions (~300 cycles: R2UR moves, constant loads, reconvergence) — more than the tensor time of a
+// k-block at BN <= 128 — so the loops below issue as much as they can per block: with resident weights all nine taps of
+// a halo chunk (plus both commits) go out under ONE elect, otherwise one block per k-block with the commits folded in.
+// (CC_DBG bisection + ncu source view, profiles/r02_issue_loop.md)
 template <int KPB>
+__device__ __forceinline__ void mma_kblock(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  umma_f16(d_tmem, adesc, bdesc, idesc, accumulate);
+#pragma unroll
+  for (int k = 1; k < KPB; ++k) umma_f16_c<true>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc);
+}
+
+template <int KPB, bool BRES>
 __device__ __forceinline__ void mma_issuer(const GemmParams& p, uint8_t* sA, uint8_t* sB, uint32_t row_bytes, uint32_t a_bytes,
                                            uint32_t b_bytes, int S, int num_kb, uint64_t* full_bar, uint64_t* empty_bar,
                                            uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* afull_bar,
@@ -101,76 +112,78 @@ __device__ __forceinline__ void mma_issuer(const GemmParams& p, uint8_t* sA, uin
     const uint64_t d_halo = dconst | (static_cast<uint64_t>((16u * row_bytes) >> 4) << 32);   // halo views: 16-px row pitch
     const uint32_t sA16 = (smem_u32(sA) & 0x3FFFF) >> 4, sB16 = (smem_u32(sB) & 0x3FFFF) >> 4;
     const uint32_t a16 = a_bytes >> 4, b16 = b_bytes >> 4, h16 = p.halo_bytes >> 4;
+    const int num_tiles = p.num_tiles, tstride = gridDim.x, cpt = p.chunks_per_tap, hstages = p.halo_stages;
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    if (p.b_res) { mbar_wait(bres_bar, 0); tc_fence_after(); }
+    if (BRES) { mbar_wait(bres_bar, 0); tc_fence_after(); }
     if (p.halo) {
       int sa = 0;
       uint32_t pa = 0;
       const uint32_t rstep16 = ((16u << p.lTN) * row_bytes) >> 4;  // one halo row block (TN images x 16 px), in 16-B units
       const uint32_t sstep16 = row_bytes >> 4;                      // one pixel
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const uint32_t btap16 = cpt * b16;                            // resident weights: descriptor step between taps
+      for (int tile = blockIdx.x; tile < num_tiles; tile += tstride) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
-        bool first = true;
-        for (int ch = 0; ch < p.chunks_per_tap; ++ch) {
+        for (int ch = 0; ch < cpt; ++ch) {
           mbar_wait(&afull_bar[sa], pa);
           tc_fence_after();
           const uint64_t a_base = d_halo | (sA16 + sa * h16);
-          for (int r = 0; r < 3; ++r)
-            for (int sx = 0; sx < 3; ++sx) {
-              const uint64_t adesc = a_base + (r * rstep16 + sx * sstep16);
-              uint64_t bdesc;
-              if (p.b_res) {
-                bdesc = d_tile | (sB16 + ((r * 3 + sx) * p.chunks_per_tap + ch) * b16);
-              } else {
-                mbar_wait(&full_bar[stage], phase);
-                tc_fence_after();
-                bdesc = d_tile | (sB16 + stage * b16);
-              }
+          if (BRES) {
+            if (elect_one()) {
+              const uint64_t b_base = d_tile | (sB16 + ch * b16);
+#pragma unroll
+              for (int t = 0; t < 9; ++t)
+                mma_kblock<KPB>(d_tmem, a_base + ((t / 3) * rstep16 + (t % 3) * sstep16), b_base + t * btap16, idesc,
+                                t == 0 ? static_cast<uint32_t>(ch != 0) : 1u);
+              umma_commit(&aempty_bar[sa]);
+              if (ch == cpt - 1) umma_commit(&tfull_bar[acc]);
+            }
+            __syncwarp();
+          } else {
+#pragma unroll 1
+            for (int t = 0; t < 9; ++t) {
+              mbar_wait(&full_bar[stage], phase);
+              tc_fence_after();
               if (elect_one()) {
-                if (first) umma_f16_c<false>(d_tmem, adesc, bdesc, idesc); else umma_f16_c<true>(d_tmem, adesc, bdesc, idesc);
-                #pragma unroll
-                for (int k = 1; k < KPB; ++k) umma_f16_c<true>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc);
-                if (!p.b_res) umma_commit(&empty_bar[stage]);
+                const int r = t / 3;
+                mma_kblock<KPB>(d_tmem, a_base + (r * rstep16 + (t - 3 * r) * sstep16), d_tile | (sB16 + stage * b16), idesc,
+                                static_cast<uint32_t>((ch | t) != 0));
+                umma_commit(&empty_bar[stage]);
+                if (t == 8) {
+                  umma_commit(&aempty_bar[sa]);
+                  if (ch == cpt - 1) umma_commit(&tfull_bar[acc]);
+                }
               }
               __syncwarp();
-              first = false;
-              if (!p.b_res) { if (++stage == S) { stage = 0; phase ^= 1; } }
+              if (++stage == S) { stage = 0; phase ^= 1; }
             }
-          if (elect_one()) umma_commit(&aempty_bar[sa]);
-          __syncwarp();
-          if (++sa == p.halo_stages) { sa = 0; pa ^= 1; }
+          }
+          if (++sa == hstages) { sa = 0; pa ^= 1; }
         }
-        if (elect_one()) umma_commit(&tfull_bar[acc]);
-        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
     } else {
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += tstride) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t adesc = d_tile | (sA16 + stage * a16);
-          const uint64_t bdesc = d_tile | (sB16 + (p.b_res ? kb : stage) * b16);
           if (elect_one()) {
-            if (kb == 0) umma_f16_c<false>(d_tmem, adesc, bdesc, idesc); else umma_f16_c<true>(d_tmem, adesc, bdesc, idesc);
-            #pragma unroll
-                for (int k = 1; k < KPB; ++k) umma_f16_c<true>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc);
-            umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs have read it
+            mma_kblock<KPB>(d_tmem, d_tile | (sA16 + stage * a16), d_tile | (sB16 + (BRES ? kb : stage) * b16), idesc,
+                            static_cast<uint32_t>(kb != 0));
+            umma_commit(&empty_bar[stage]);                         // frees this smem stage once the MMAs have read it
+            if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);     // accumulator complete -> epilogue
           }
           __syncwarp();
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
-        if (elect_one()) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
-        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -225,7 +238,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], p.epi_threads);
+      mbar_init(&tempty_bar[i], p.epi_threads >> 5);   // one arrival per epilogue warp
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&afull_bar[i], 1);
@@ -274,8 +287,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           const int nb = tx.nb, w0 = tx.w0, h0 = tx.h0, n0 = tx.n0;
           for (int ch = 0; ch < p.chunks_per_tap; ++ch) {
             mbar_wait(&aempty_bar[sa], pa ^ 1);
+            if (p.dbg & 4) mbar_arrive(&afull_bar[sa]);
+            else {
             mbar_arrive_expect_tx(&afull_bar[sa], p.halo_bytes);
             tma_load_5d(sA + sa * p.halo_bytes, &p.tmA, &afull_bar[sa], ch * p.BK, w0 - 1, n0, h0 - 1, 0);
+            }
             if (++sa == p.halo_stages) { sa = 0; pa ^= 1; }
             if (!p.b_res)
             for (int t = 0; t < 9; ++t) {
@@ -299,7 +315,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           const int c4 = p.s2 ? n0 : 0;
           for (int ch = 0; ch < p.chunks_per_tap; ++ch, ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[stage], p.b_res ? a_bytes : a_bytes + b_bytes);
+            mbar_arrive_expect_tx(&full_bar[stage], (p.dbg & 4) ? (p.b_res ? 0 : b_bytes) : (p.b_res ? a_bytes : a_bytes + b_bytes));
+            if (!(p.dbg & 4))
             tma_load_5d(sA + stage * a_bytes, &p.tmA, &full_bar[stage], c_base + ch * p.BK, c1, c2, c3, c4);
             if (!p.b_res) tma_load_2d(sB + stage * b_bytes, &p.tmB, &full_bar[stage], kb * p.BK, nb * p.BN);
             if (++stage == S) { stage = 0; phase ^= 1; }
@@ -309,9 +326,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (p.BK == 64) mma_issuer<4>(p, sA, sB, row_bytes, a_bytes, b_bytes, S, num_kb, full_bar, empty_bar, tfull_bar, tempty_bar, afull_bar, aempty_bar, bres_bar, tmem_base);
-    else if (p.BK == 32) mma_issuer<2>(p, sA, sB, row_bytes, a_bytes, b_bytes, S, num_kb, full_bar, empty_bar, tfull_bar, tempty_bar, afull_bar, aempty_bar, bres_bar, tmem_base);
-    else mma_issuer<1>(p, sA, sB, row_bytes, a_bytes, b_bytes, S, num_kb, full_bar, empty_bar, tfull_bar, tempty_bar, afull_bar, aempty_bar, bres_bar, tmem_base);
+#define CC_ISSUE(KPB) \
+    do { if (p.b_res) mma_issuer<KPB, true>(p, sA, sB, row_bytes, a_bytes, b_bytes, S, num_kb, full_bar, empty_bar, tfull_bar, tempty_bar, afull_bar, aempty_bar, bres_bar, tmem_base); \
+         else mma_issuer<KPB, false>(p, sA, sB, row_bytes, a_bytes, b_bytes, S, num_kb, full_bar, empty_bar, tfull_bar, tempty_bar, afull_bar, aempty_bar, bres_bar, tmem_base); } while (0)
+    if (p.BK == 64) CC_ISSUE(4);
+    else if (p.BK == 32) CC_ISSUE(2);
+    else CC_ISSUE(1);
+#undef CC_ISSUE
   } else if (warp >= 4 && warp < 4 + (p.epi_threads >> 5)) {
     // (narrow tiles: warps without a 16-column chunk to convert sit the kernel out instead of paying the per-tile
     //  bookkeeping and barriers)
@@ -367,6 +388,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
+      if (p.dbg & 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        continue;
+      }
       const uint32_t t_row = tmem_base + acc * 256 + (static_cast<uint32_t>(ew * 32) << 16);
 
       for (int cc0 = 0; cc0 < p.BN; cc0 += CH) {
@@ -481,9 +510,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           }
         }
         if (cc0 + CH >= p.BN) {
-          // all TMEM reads of this accumulator done -> hand it back to the MMA warp
+          // all TMEM reads of this accumulator done -> hand it back to the MMA warp.  ONE arrival per warp: 512 threads
+          // arriving on the same mbarrier serialise in the LSU (~2.5k cycles per tile, the floor of every small layer
+          // before this change; CC_DBG bisection, profiles/r02)
           tc_fence_before();
-          mbar_arrive(&tempty_bar[acc]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
         if (p.tma_store) {
           fence_proxy_async_smem();        // generic-proxy smem writes -> visible to the TMA (async proxy)
@@ -762,6 +794,8 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
   int S;
   static const int bres_env = getenv("CC_BRES") ? atoi(getenv("CC_BRES")) : 1;
   static const int epidyn_env = getenv("CC_EPI_DYN") ? atoi(getenv("CC_EPI_DYN")) : 1;
+  static const int dbg_env = getenv("CC_DBG") ? atoi(getenv("CC_DBG")) : 0;
+  p.dbg = dbg_env;
   {
     auto fast_div = [](uint32_t d, uint32_t fd[2]) {      // q = (umulhi(mul, x) + x) >> shift for x < 2^31
       uint32_t l = 0;

@@ -51,6 +51,7 @@ struct GemmParams {
   // math was ~140 of the ~260 instructions every epilogue warp spends per tile; ncu profiles/r02)
   uint32_t fd_nb[2], fd_tw[2], fd_th[2], fd_twh[2];
   int32_t stg_lrow;                   // log2 of the staging / TMA-store row: 7 (SWIZZLE_128B) or 6 (SWIZZLE_64B, narrow tiles)
+  int32_t dbg;                        // CC_DBG bisection switches (never set in production): 1 no epilogue work, 4 no A loads
   int32_t epi_threads;                // epilogue threads that have columns to convert: 128 * min(4, BN/16)
 };
 
