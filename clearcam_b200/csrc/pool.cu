@@ -47,138 +47,186 @@ static int grid_for(long long total, int threads) {
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < (total); \
        idx += static_cast<long long>(gridDim.x) * blockDim.x)
 
+// Row-structured launches for the pools: blockIdx.z = image, blockIdx.y = output row, x covers (pixel, 8-channel vector)
+// of that row with 32-bit index math.  The first version decoded a flat 64-bit index per element — four 64-bit divisions,
+// several hundred instructions, more than the actual work of a pool; the kernels were instruction-bound at 1.4-3 TB/s.
+struct RowIdx { int n, h, w, c; bool ok; };
+__device__ __forceinline__ RowIdx row_index(int W, int c8) {
+  RowIdx r;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  r.n = blockIdx.z;
+  r.h = blockIdx.y;
+  r.w = i / c8;
+  r.c = (i - r.w * c8) * 8;
+  r.ok = r.w < W;
+  return r;
+}
+static dim3 row_grid(const TSlice& out, int threads) {
+  const int per_row = out.W * (out.C / 8);
+  return dim3((per_row + threads - 1) / threads, out.H, out.N);
+}
+static int row_threads(const TSlice& out) {
+  const int per_row = out.W * (out.C / 8);
+  return per_row >= 256 ? 256 : (per_row >= 128 ? 128 : 64);
+}
+
 // ---------------------------------------------------------------- avg 2x2 s1 -> same-size zero-edged map
 __global__ void avgpool2_pad_kernel(TSlice in, TSlice out) {
-  const int c8 = in.C / 8;
-  const long long total = static_cast<long long>(out.N) * out.H * out.W * c8;
-  CC_GRID_STRIDE(idx, total) {
-    const int c = static_cast<int>(idx % c8) * 8;
-    long long pix = idx / c8;
-    const int w = static_cast<int>(pix % out.W);
-    const int h = static_cast<int>((pix / out.W) % out.H);
-    const int n = static_cast<int>(pix / (static_cast<long long>(out.W) * out.H));
-    bf8 r;
-    if (h < in.H - 1 && w < in.W - 1) {
-      const bf8 a = ld8(at(in, n, h, w, c)), b = ld8(at(in, n, h, w + 1, c));
-      const bf8 d = ld8(at(in, n, h + 1, w, c)), e = ld8(at(in, n, h + 1, w + 1, c));
+  const RowIdx q = row_index(out.W, in.C / 8);
+  if (!q.ok) return;
+  bf8 r;
+  if (q.h < in.H - 1 && q.w < in.W - 1) {
+    const __nv_bfloat16* p0 = at(in, q.n, q.h, q.w, q.c);
+    const __nv_bfloat16* p1 = p0 + static_cast<long long>(in.W) * in.cs;
+    const bf8 a = ld8(p0), b = ld8(p0 + in.cs), d = ld8(p1), e = ld8(p1 + in.cs);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) r.v[i] = ((a.v[i] + b.v[i]) + (d.v[i] + e.v[i])) * 0.25f;
-    } else {
+    for (int i = 0; i < 8; ++i) r.v[i] = ((a.v[i] + b.v[i]) + (d.v[i] + e.v[i])) * 0.25f;
+  } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) r.v[i] = 0.f;
-    }
-    st8(at_w(out, n, h, w, c), r);
+    for (int i = 0; i < 8; ++i) r.v[i] = 0.f;
   }
+  st8(at_w(out, q.n, q.h, q.w, q.c), r);
 }
 int avgpool2_pad_launch(const TSlice& in, const TSlice& out, cudaStream_t s) {
   CC_REQUIRE(in.C % 8 == 0 && in.co % 8 == 0 && in.cs % 8 == 0 && out.co % 8 == 0 && out.cs % 8 == 0 && in.C == out.C &&
                  in.H == out.H && in.W == out.W, "avgpool2_pad: bad slices");
-  const long long total = static_cast<long long>(out.N) * out.H * out.W * (in.C / 8);
-  avgpool2_pad_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, out);
+  CC_REQUIRE(out.H <= 65535 && out.N <= 65535, "avgpool2_pad: tensor too large for the row grid");
+  const int t = row_threads(out);
+  avgpool2_pad_kernel<<<row_grid(out, t), t, 0, s>>>(in, out);
   CC_CHECK_CUDA(cudaGetLastError());
   return CC_OK;
 }
 
 // ---------------------------------------------------------------- max3x3 s2 p1 of avg2x2 s1 (ADown branch 2)
-__global__ void avgmax_pool_kernel(TSlice in, TSlice out) {
-  const int c8 = in.C / 8;
-  const int Ha = in.H - 1, Wa = in.W - 1;  // extent of the (virtual) avg-pooled map
-  const long long total = static_cast<long long>(out.N) * out.H * out.W * c8;
-  CC_GRID_STRIDE(idx, total) {
-    const int c = static_cast<int>(idx % c8) * 8;
-    long long pix = idx / c8;
-    const int ox = static_cast<int>(pix % out.W);
-    const int oy = static_cast<int>((pix / out.W) % out.H);
-    const int n = static_cast<int>(pix / (static_cast<long long>(out.W) * out.H));
-    bf8 m;
+// Output (oy, ox) = max over the avg map at rows 2oy-1..2oy+1, cols 2ox-1..2ox+1 (inside the (H-1)x(W-1) avg map), each
+// avg = ((a+b)+(d+e))*0.25 rounded to bf16 first (the reference max-pools the stored avg map).  Separable: the row-pair
+// sums (a+b) are shared by vertically adjacent averages, so the 4x4 input window is read once (16 vector loads instead of
+// 36) and the additions keep the reference's order.
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-    for (int i = 0; i < 8; ++i) m.v[i] = -INFINITY;
-    // avg rows 2oy-1..2oy+1 need input rows 2oy-1..2oy+2
-    const int y0 = 2 * oy - 1, x0 = 2 * ox - 1;
-    for (int ay = 0; ay < 3; ++ay) {
-      const int y = y0 + ay;
-      if (y < 0 || y >= Ha) continue;
-      for (int ax = 0; ax < 3; ++ax) {
-        const int x = x0 + ax;
-        if (x < 0 || x >= Wa) continue;
-        const bf8 a = ld8(at(in, n, y, x, c)), b = ld8(at(in, n, y, x + 1, c));
-        const bf8 d = ld8(at(in, n, y + 1, x, c)), e = ld8(at(in, n, y + 1, x + 1, c));
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);           // bf16 -> fp32 is a shift
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+  }
+}
+__global__ void __launch_bounds__(256, 2) avgmax_pool_kernel(TSlice in, TSlice out) {
+  const RowIdx q = row_index(out.W, in.C / 8);
+  if (!q.ok) return;
+  const int Ha = in.H - 1, Wa = in.W - 1;
+  const int y0 = 2 * q.h - 1, x0 = 2 * q.w - 1;
+  // all 16 vector loads of the 4x4 window go out first (clamped coordinates: always in bounds, never used when the
+  // position is outside the map) — the kernel is latency-bound, so bytes in flight per SM are what buys bandwidth
+  uint4 raw[4][4];
+  const __nv_bfloat16* base = at(in, q.n, 0, 0, q.c);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          // round the average to bf16 first: the reference max-pools the stored avg map
-          const float av = __bfloat162float(__float2bfloat16_rn(((a.v[i] + b.v[i]) + (d.v[i] + e.v[i])) * 0.25f));
-          m.v[i] = fmaxf(m.v[i], av);
+  for (int r = 0; r < 4; ++r) {
+    const int y = min(max(y0 + r, 0), in.H - 1);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int x = min(max(x0 + c, 0), in.W - 1);
+      raw[r][c] = __ldg(reinterpret_cast<const uint4*>(base + (static_cast<long long>(y) * in.W + x) * in.cs));
+    }
+  }
+  bool cv[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) cv[c] = (x0 + c >= 0) && (x0 + c < Wa);
+  float m[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
+  float hp[3][8];                    // row-pair sums (a+b) of the previous input row
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    float v0[8], v1[8], v2[8], v3[8], h[3][8];
+    unpack8(raw[r][0], v0);
+    unpack8(raw[r][1], v1);
+    unpack8(raw[r][2], v2);
+    unpack8(raw[r][3], v3);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      h[0][i] = v0[i] + v1[i];
+      h[1][i] = v1[i] + v2[i];
+      h[2][i] = v2[i] + v3[i];
+    }
+    if (r >= 1) {
+      const int ya = y0 + r - 1;     // avg row = input rows (ya, ya+1)
+      if (ya >= 0 && ya < Ha) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          if (cv[c]) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float av = __bfloat162float(__float2bfloat16_rn((hp[c][i] + h[c][i]) * 0.25f));
+              m[i] = fmaxf(m[i], av);
+            }
+          }
         }
       }
     }
-    st8(at_w(out, n, oy, ox, c), m);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) hp[c][i] = h[c][i];
   }
+  bf8 o;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o.v[i] = m[i];
+  st8(at_w(out, q.n, q.h, q.w, q.c), o);
 }
 int avgmax_pool_launch(const TSlice& in, const TSlice& out, cudaStream_t s) {
   CC_REQUIRE(in.C % 8 == 0 && in.co % 8 == 0 && in.cs % 8 == 0 && out.co % 8 == 0 && out.cs % 8 == 0 && in.C == out.C,
              "avgmax_pool: bad slices");
   CC_REQUIRE(out.H == (in.H - 1 + 2 - 3) / 2 + 1 && out.W == (in.W - 1 + 2 - 3) / 2 + 1, "avgmax_pool: bad output extent");
-  const long long total = static_cast<long long>(out.N) * out.H * out.W * (in.C / 8);
-  avgmax_pool_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, out);
+  CC_REQUIRE(out.H <= 65535 && out.N <= 65535, "avgmax_pool: tensor too large for the row grid");
+  const int t = row_threads(out);
+  avgmax_pool_kernel<<<row_grid(out, t), t, 0, s>>>(in, out);
   CC_CHECK_CUDA(cudaGetLastError());
   return CC_OK;
 }
 
 // ---------------------------------------------------------------- max 5x5 s1 p2
 __global__ void maxpool5_kernel(TSlice in, TSlice out) {
-  const int c8 = in.C / 8;
-  const long long total = static_cast<long long>(out.N) * out.H * out.W * c8;
-  CC_GRID_STRIDE(idx, total) {
-    const int c = static_cast<int>(idx % c8) * 8;
-    long long pix = idx / c8;
-    const int w = static_cast<int>(pix % out.W);
-    const int h = static_cast<int>((pix / out.W) % out.H);
-    const int n = static_cast<int>(pix / (static_cast<long long>(out.W) * out.H));
-    bf8 m;
+  const RowIdx q = row_index(out.W, in.C / 8);
+  if (!q.ok) return;
+  bf8 m;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) m.v[i] = -INFINITY;
-    for (int dy = -2; dy <= 2; ++dy) {
-      const int y = h + dy;
-      if (y < 0 || y >= in.H) continue;
-      for (int dx = -2; dx <= 2; ++dx) {
-        const int x = w + dx;
-        if (x < 0 || x >= in.W) continue;
-        const bf8 a = ld8(at(in, n, y, x, c));
+  for (int i = 0; i < 8; ++i) m.v[i] = -INFINITY;
+  for (int dy = -2; dy <= 2; ++dy) {
+    const int y = q.h + dy;
+    if (y < 0 || y >= in.H) continue;
+    for (int dx = -2; dx <= 2; ++dx) {
+      const int x = q.w + dx;
+      if (x < 0 || x >= in.W) continue;
+      const bf8 a = ld8(at(in, q.n, y, x, q.c));
 #pragma unroll
-        for (int i = 0; i < 8; ++i) m.v[i] = fmaxf(m.v[i], a.v[i]);
-      }
+      for (int i = 0; i < 8; ++i) m.v[i] = fmaxf(m.v[i], a.v[i]);
     }
-    st8(at_w(out, n, h, w, c), m);
   }
+  st8(at_w(out, q.n, q.h, q.w, q.c), m);
 }
 int maxpool5_launch(const TSlice& in, const TSlice& out, cudaStream_t s) {
   CC_REQUIRE(in.C % 8 == 0 && in.co % 8 == 0 && in.cs % 8 == 0 && out.co % 8 == 0 && out.cs % 8 == 0 && in.C == out.C &&
                  in.H == out.H && in.W == out.W, "maxpool5: bad slices");
-  const long long total = static_cast<long long>(out.N) * out.H * out.W * (in.C / 8);
-  maxpool5_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, out);
+  CC_REQUIRE(out.H <= 65535 && out.N <= 65535, "maxpool5: tensor too large for the row grid");
+  const int t = row_threads(out);
+  maxpool5_kernel<<<row_grid(out, t), t, 0, s>>>(in, out);
   CC_CHECK_CUDA(cudaGetLastError());
   return CC_OK;
 }
 
 // ---------------------------------------------------------------- nearest x2
 __global__ void upsample2_kernel(TSlice in, TSlice out) {
-  const int c8 = in.C / 8;
-  const long long total = static_cast<long long>(out.N) * out.H * out.W * c8;
-  CC_GRID_STRIDE(idx, total) {
-    const int c = static_cast<int>(idx % c8) * 8;
-    long long pix = idx / c8;
-    const int w = static_cast<int>(pix % out.W);
-    const int h = static_cast<int>((pix / out.W) % out.H);
-    const int n = static_cast<int>(pix / (static_cast<long long>(out.W) * out.H));
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(at(in, n, h >> 1, w >> 1, c)));
-    *reinterpret_cast<uint4*>(at_w(out, n, h, w, c)) = v;
-  }
+  const RowIdx q = row_index(out.W, in.C / 8);
+  if (!q.ok) return;
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(at(in, q.n, q.h >> 1, q.w >> 1, q.c)));
+  *reinterpret_cast<uint4*>(at_w(out, q.n, q.h, q.w, q.c)) = v;
 }
 int upsample2_launch(const TSlice& in, const TSlice& out, cudaStream_t s) {
   CC_REQUIRE(in.C % 8 == 0 && in.co % 8 == 0 && in.cs % 8 == 0 && out.co % 8 == 0 && out.cs % 8 == 0 && in.C == out.C &&
                  out.H == 2 * in.H && out.W == 2 * in.W, "upsample2: bad slices");
-  const long long total = static_cast<long long>(out.N) * out.H * out.W * (in.C / 8);
-  upsample2_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, out);
+  CC_REQUIRE(out.H <= 65535 && out.N <= 65535, "upsample2: tensor too large for the row grid");
+  const int t = row_threads(out);
+  upsample2_kernel<<<row_grid(out, t), t, 0, s>>>(in, out);
   CC_CHECK_CUDA(cudaGetLastError());
   return CC_OK;
 }
