@@ -52,7 +52,11 @@ static bool build_spec(const std::string& size, std::vector<Layer>* out) {
       {"t", {16, 64, 96, 24, 128, 256, 224, 160, 48, 144, 192, 80, 32, 16, 3, 96, 32, 64, 128, 64, 64, 128}},
       {"s", {32, 128, 192, 48, 256, 512, 448, 320, 96, 288, 384, 128, 64, 32, 3, 192, 64, 64, 128, 128, 128, 256}},
       {"m", {32, 240, 360, 90, 480, 960, 840, 600, 184, 544, 720, 240, 128, 60, 1, 360, 120, 64, 128, 240, 240, 480}},
-      {"c", {64, 256, 512, 128, 256, 1024, 1024, 1024, 128, 768, 1024, 256, 128, 64, 1, 256, 128, 128, 256, 128, 512, 512}}};
+      {"c", {64, 256, 512, 128, 256, 1024, 1024, 1024, 128, 768, 1024, 256, 128, 64, 1, 256, 128, 128, 256, 128, 512, 512}},
+      // zero-padded equivalents of t and m (every width a multiple of 16): same graphs, weights scattered into the padded
+      // layout by the host (clearcam_b200/detection/padding.py; the function computed is unchanged, tests/test_oracle_cpu.py)
+      {"t@16", {16, 64, 96, 32, 128, 256, 224, 160, 48, 144, 192, 80, 32, 16, 3, 96, 32, 64, 128, 64, 64, 128}},
+      {"m@16", {32, 240, 384, 96, 480, 960, 864, 624, 192, 576, 720, 240, 128, 64, 1, 384, 128, 64, 128, 240, 240, 480}}};
   if (size == "e") {
     L.push_back(mk(L_SILENCE));
     L.push_back(conv_l(3, 64, 3, 2));
@@ -105,7 +109,8 @@ static bool build_spec(const std::string& size, std::vector<Layer>* out) {
   const int a = z[0], b = z[1], c = z[2], d = z[3], e = z[4], f = z[5], g = z[6], h = z[7], i = z[8], j = z[9], k = z[10],
             l = z[11], m = z[12], n = z[13], p = z[14], q = z[15], r = z[16], s = z[17], t = z[18], u = z[19], v = z[20],
             w = z[21];
-  const bool small = size == "t" || size == "s";
+  const std::string base = size.substr(0, size.find('@'));
+  const bool small = base == "t" || base == "s";
   const bool isc = size == "c";
   L.push_back(conv_l(3, a, 3, 2));
   L.push_back(conv_l(a, a * 2, 3, 2));

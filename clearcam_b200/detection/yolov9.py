@@ -21,6 +21,7 @@ from typing import Dict, Optional
 import numpy as np
 import torch
 
+from . import padding
 from .._lib import CCError, check, lib, ptr, stream_ptr
 
 
@@ -128,8 +129,10 @@ def postprocess(output, max_det=300, conf_threshold=0.25, iou_threshold=0.45):
 class YOLOv9:
     """YOLOv9(size, res) — same constructor/call contract as the reference (detection/yolov9.py:298-388)."""
 
-    def __init__(self, size: str = "t", res: int = 1280, weights=None):
-        self.size, self.res = size, res
+    def __init__(self, size: str = "t", res: int = 1280, weights=None, pad: bool = True):
+        """pad=False keeps a size with odd widths (t) on its literal graph, whose narrow convs then take the generic
+        CUDA-core kernel; m only runs padded."""
+        self.size, self.res, self.pad = size, res, pad
         self._h = None
         if weights is None:
             weights = safe_load(fetch(f"https://huggingface.co/roryclear/yolov9/resolve/main/yolov9-{size}.safetensors"))
@@ -143,13 +146,18 @@ class YOLOv9:
         n = L.cc_device_check()
         if n <= 0:
             raise CCError("clearcam_b200 needs a B200 (sm_100) GPU: " + L.cc_last_error().decode())
-        items = [(k.replace(".list.", "."), _to_host_fp32(v)) for k, v in state_dict.items()
-                 if not k.endswith(("anchors", "strides"))]
+        sd = {k.replace(".list.", "."): _to_host_fp32(v) for k, v in state_dict.items() if not k.endswith(("anchors", "strides"))}
+        lib_size = self.size
+        if self.pad and padding.padded_size(self.size):
+            # t and m have widths that are not multiples of 16: run their zero-padded equivalents (same function,
+            # every conv on the tensor-core kernel) — see detection/padding.py
+            sd, lib_size = padding.pad_state_dict(self.size, sd), padding.padded_size(self.size)
+        items = list(sd.items())
         names = (ctypes.c_char_p * len(items))(*[k.encode() for k, _ in items])
         ptrs = (ctypes.c_void_p * len(items))(*[a.ctypes.data for _, a in items])
         nums = (ctypes.c_int64 * len(items))(*[a.size for _, a in items])
         h = ctypes.c_void_p()
-        check(L.cc_yolo_create(self.size.encode(), len(items), names, ptrs, nums, ctypes.byref(h)), "cc_yolo_create")
+        check(L.cc_yolo_create(lib_size.encode(), len(items), names, ptrs, nums, ctypes.byref(h)), "cc_yolo_create")
         if self._h is not None:
             L.cc_yolo_destroy(self._h)
         self._h = h
@@ -282,6 +290,15 @@ class YOLOv9:
         out = torch.empty(B, hh.value, ww.value, c.value, device="cuda", dtype=torch.float32)
         check(lib().cc_yolo_layer_output(self._h, f, B, Hf, Wf, self.res, layer, ptr(out), ctypes.byref(c),
                                          ctypes.byref(hh), ctypes.byref(ww), stream_ptr()), "cc_yolo_layer_output")
+        if self.pad and padding.padded_size(self.size):        # padded equivalent: report the model's own channels
+            maps = padding.layer_channel_maps(self.size)
+            if layer < len(maps):
+                idx = torch.from_numpy(maps[layer]).cuda()
+                pads = torch.ones(c.value, dtype=torch.bool, device="cuda")
+                pads[idx] = False
+                if bool(pads.any()) and float(out[..., pads].abs().max()) != 0.0:
+                    raise CCError(f"layer {layer}: padding channels are not zero")
+                out = out[..., idx]
         return out.permute(0, 3, 1, 2)
 
     # -- host-side helpers kept for API parity

@@ -31,6 +31,10 @@ _SIZES = {
     "s": [32, 128, 192, 48, 256, 512, 448, 320, 96, 288, 384, 128, 64, 32, 3, 192, 64, 64, 128, 128, 128, 256],
     "m": [32, 240, 360, 90, 480, 960, 840, 600, 184, 544, 720, 240, 128, 60, 1, 360, 120, 64, 128, 240, 240, 480],
     "c": [64, 256, 512, 128, 256, 1024, 1024, 1024, 128, 768, 1024, 256, 128, 64, 1, 256, 128, 128, 256, 128, 512, 512],
+    # zero-padded equivalents the CUDA path runs t and m as (clearcam_b200/detection/padding.py): same graph, widths
+    # rounded up to multiples of 16; tests/test_oracle_cpu.py proves the weight transform leaves the function unchanged
+    "t@16": [16, 64, 96, 32, 128, 256, 224, 160, 48, 144, 192, 80, 32, 16, 3, 96, 32, 64, 128, 64, 64, 128],
+    "m@16": [32, 240, 384, 96, 480, 960, 864, 624, 192, 576, 720, 240, 128, 64, 1, 384, 128, 64, 128, 240, 240, 480],
 }
 
 
@@ -54,7 +58,7 @@ def build_spec(size: str) -> List[dict]:
     L: List[dict] = []
     if size != "e":
         a, b, c, d, e, f, g, h, i, j, k, l, m, n, p, q, r, s, t, u, v, w = _SIZES[size]
-        small = size in ("t", "s")
+        small = size.split("@")[0] in ("t", "s")
         L.append({**_conv(3, a, 3, 2), "f": -1})
         L.append({**_conv(a, a * 2, 3, 2), "f": -1})
         L.append({"op": "elan1", "ch0": a * 2, "ch1": m, "ch2": a, "ch3": b, "f": -1} if small else _elan4(s, 32, t, p))

@@ -181,3 +181,31 @@ def test_fp32_noise_floor_of_the_reference_arithmetic():
     d = (r32.double() - r64).abs()
     assert d[:, :4].max() > 1e-3, "fp32 and fp64 evaluation agree to 1e-3 px?"
     assert d[:, :4].mean() < 1e-3 and d[:, 4:].max() < 1e-4
+
+
+@pytest.mark.parametrize("size", ["t", "m"])
+def test_zero_padded_equivalent_computes_the_same_function(size):
+    """YOLOv9-t / -m run on the GPU as their zero-padded equivalents (widths rounded up to multiples of 16, weights scattered
+    by clearcam_b200/detection/padding.py).  The oracle evaluates both the reference-shaped and the padded model: the
+    head tensors and the detections agree to fp32 summation order."""
+    from clearcam_b200.detection.padding import pad_state_dict, padded_size, layer_channel_maps, PADDED
+    torch.set_num_threads(min(8, torch.get_num_threads()))
+    fr = o.synthetic_frames(2, 128, 160, seed=3)
+    x = fr.flip(-1).permute(0, 3, 1, 2).float() / 255
+    P = o.synthetic_weights(size, seed=1, calib=x[:1])
+    P16 = {k: torch.from_numpy(np.asarray(v)) for k, v in pad_state_dict(size, {k: v.numpy() for k, v in P.items()}).items()}
+    taps, taps16 = [], []
+    with torch.no_grad():
+        y = o.forward_raw(size, P, x, taps=taps)
+        y16 = o.forward_raw(padded_size(size), P16, x, taps=taps16)
+    assert float((y - y16).abs().max()) <= 2e-5 * float(y.abs().max())
+    maps = layer_channel_maps(size)
+    for i, idx in enumerate(maps):                      # every layer: real channels equal, padding channels exactly zero
+        a, b = taps[i], taps16[i]
+        assert torch.allclose(b[:, torch.from_numpy(idx)], a, rtol=1e-4, atol=1e-4 * float(a.abs().max())), f"layer {i}"
+        pad = torch.ones(b.shape[1], dtype=torch.bool)
+        pad[torch.from_numpy(idx)] = False
+        assert float(b[:, pad].abs().max()) == 0.0 if pad.any() else True
+    assert all(v % 16 == 0 for k, v in zip("abcdefghijklmnpqrstuvw", PADDED[size]) if k not in "p")
+    d, d16 = o.detect(size, P, fr, 128), o.detect(padded_size(size), P16, fr, 128)
+    assert float((d - d16).abs().max()) < 1e-2
