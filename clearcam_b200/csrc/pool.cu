@@ -233,35 +233,29 @@ int upsample2_launch(const TSlice& in, const TSlice& out, cudaStream_t s) {
 
 // ---------------------------------------------------------------- CBFuse
 __global__ void cbfuse_kernel(CBFuseParams p) {
-  const int c8 = p.out.C / 8;
-  const long long total = static_cast<long long>(p.out.N) * p.out.H * p.out.W * c8;
-  CC_GRID_STRIDE(idx, total) {
-    const int c = static_cast<int>(idx % c8) * 8;
-    long long pix = idx / c8;
-    const int w = static_cast<int>(pix % p.out.W);
-    const int h = static_cast<int>((pix / p.out.W) % p.out.H);
-    const int n = static_cast<int>(pix / (static_cast<long long>(p.out.W) * p.out.H));
-    bf8 acc;
+  const RowIdx q = row_index(p.out.W, p.out.C / 8);
+  if (!q.ok) return;
+  bf8 acc;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc.v[i] = 0.f;
-    for (int k = 0; k < p.nsrc; ++k) {
-      // nearest: src = floor(dst * in / out)
-      const int sh = static_cast<int>((static_cast<long long>(h) * p.src[k].H) / p.out.H);
-      const int sw = static_cast<int>((static_cast<long long>(w) * p.src[k].W) / p.out.W);
-      const bf8 a = ld8(at(p.src[k], n, sh, sw, c));
+  for (int i = 0; i < 8; ++i) acc.v[i] = 0.f;
+  for (int k = 0; k < p.nsrc; ++k) {
+    // nearest: src = floor(dst * in / out)
+    const int sh = (q.h * p.src[k].H) / p.out.H;
+    const int sw = (q.w * p.src[k].W) / p.out.W;
+    const bf8 a = ld8(at(p.src[k], q.n, sh, sw, q.c));
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc.v[i] = (k == 0) ? a.v[i] : acc.v[i] + a.v[i];
-    }
-    const bf8 l = ld8(at(p.last, n, h, w, c));
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc.v[i] += l.v[i];
-    st8(at_w(p.out, n, h, w, c), acc);
+    for (int i = 0; i < 8; ++i) acc.v[i] = (k == 0) ? a.v[i] : acc.v[i] + a.v[i];
   }
+  const bf8 l = ld8(at(p.last, q.n, q.h, q.w, q.c));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc.v[i] += l.v[i];
+  st8(at_w(p.out, q.n, q.h, q.w, q.c), acc);
 }
 int cbfuse_launch(const CBFuseParams& p, cudaStream_t s) {
   CC_REQUIRE(p.nsrc >= 1 && p.nsrc <= 5 && p.out.C % 8 == 0, "cbfuse: bad params");
-  const long long total = static_cast<long long>(p.out.N) * p.out.H * p.out.W * (p.out.C / 8);
-  cbfuse_kernel<<<grid_for(total, 256), 256, 0, s>>>(p);
+  CC_REQUIRE(p.out.H <= 65535 && p.out.N <= 65535, "cbfuse: tensor too large for the row grid");
+  const int t = row_threads(p.out);
+  cbfuse_kernel<<<row_grid(p.out, t), t, 0, s>>>(p);
   CC_CHECK_CUDA(cudaGetLastError());
   return CC_OK;
 }

@@ -251,6 +251,15 @@ struct YoloModel {
 };
 
 static bool tc_ok(int cin, int cout) { return cin % 16 == 0 && cout % 16 == 0; }
+// The two first convs of a detect-head scale read the same input and are fused into one conv of 64 + d output channels —
+// unless that sum only tiles in narrow blocks (the conv kernel tiles Cout by its largest divisor that is a multiple of 16
+// and at most 256: 64 + 240 = 304 = 16 x 19 would run 19 blocks of 16, measured 7 ms of a 14 ms YOLOv9-m step).
+static bool head_fuse_ok(int d) {
+  const int c = 64 + d;
+  for (int bn = (c < 256 ? c : 256) & ~15; bn >= 64; bn -= 16)
+    if (c % bn == 0) return true;
+  return false;
+}
 
 // ------------------------------------------------------------------------------------------------ plan builder
 struct Builder {
@@ -568,7 +577,12 @@ int Builder::build() {
           const std::string hp = pfx;
           const std::string sq = std::to_string(q);
           T t0 = talloc(64 + d, x.H, x.W);                     // [box branch 64 | class branch d]
-          conv(hp + ".cv2+cv3." + sq + ".0", x, t0, 1, CC_ACT_SILU);
+          if (head_fuse_ok(d)) {
+            conv(hp + ".cv2+cv3." + sq + ".0", x, t0, 1, CC_ACT_SILU);
+          } else {
+            conv(hp + ".cv2." + sq + ".0", x, slice(t0, 0, 64), 1, CC_ACT_SILU);
+            conv(hp + ".cv3." + sq + ".0", x, slice(t0, 64, d), 1, CC_ACT_SILU);
+          }
           T tb = talloc(64, x.H, x.W), tc = talloc(d, x.H, x.W);
           conv(hp + ".cv2." + sq + ".1", slice(t0, 0, 64), tb, 1, CC_ACT_SILU);
           conv(hp + ".cv3." + sq + ".1", slice(t0, 64, d), tc, 1, CC_ACT_SILU);
@@ -718,7 +732,12 @@ int cc_yolo_create(const char* size, int n_tensors, const char* const* names, co
       case L_DETECT:
         for (int q = 0; q < 3; ++q) {
           const std::string sq = std::to_string(q);
-          L(p + ".cv2+cv3." + sq + ".0", {p + ".cv2." + sq + ".0.conv", p + ".cv3." + sq + ".0.conv"}, l.list[q], {64, l.a}, 3);
+          if (head_fuse_ok(l.a)) {
+            L(p + ".cv2+cv3." + sq + ".0", {p + ".cv2." + sq + ".0.conv", p + ".cv3." + sq + ".0.conv"}, l.list[q], {64, l.a}, 3);
+          } else {
+            L(p + ".cv2." + sq + ".0", {p + ".cv2." + sq + ".0.conv"}, l.list[q], {64}, 3);
+            L(p + ".cv3." + sq + ".0", {p + ".cv3." + sq + ".0.conv"}, l.list[q], {l.a}, 3);
+          }
           L(p + ".cv2." + sq + ".1", {p + ".cv2." + sq + ".1.conv"}, 64, {64}, 3, 4);
           L(p + ".cv2." + sq + ".2", {p + ".cv2." + sq + ".2"}, 64, {64}, 1, 4);
           L(p + ".cv3." + sq + ".1", {p + ".cv3." + sq + ".1.conv"}, l.a, {l.a}, 3);
