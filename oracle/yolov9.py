@@ -33,7 +33,7 @@ _SIZES = {
     "c": [64, 256, 512, 128, 256, 1024, 1024, 1024, 128, 768, 1024, 256, 128, 64, 1, 256, 128, 128, 256, 128, 512, 512],
     # zero-padded equivalents the CUDA path runs t and m as (clearcam_b200/detection/padding.py): same graph, widths
     # rounded up to multiples of 16; tests/test_oracle_cpu.py proves the weight transform leaves the function unchanged
-    "t@16": [16, 64, 96, 32, 128, 256, 224, 160, 48, 144, 192, 80, 32, 16, 3, 96, 32, 64, 128, 64, 64, 128],
+    "t@16": [16, 64, 96, 32, 128, 256, 224, 160, 48, 144, 192, 96, 32, 16, 3, 96, 32, 64, 128, 64, 64, 128],
     "m@16": [32, 240, 384, 96, 480, 960, 864, 624, 192, 576, 720, 240, 128, 64, 1, 384, 128, 64, 128, 240, 240, 480],
 }
 
