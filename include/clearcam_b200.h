@@ -48,7 +48,11 @@ int cc_conv2d(const void* d_in, int N, int Hin, int Win, int in_cs, int in_co, i
 /* ---- YOLOv9 detector (replaces detection/yolov9.py: class YOLOv9, :298-458) ---- */
 typedef struct cc_yolo cc_yolo;
 
-/* size: "t"|"s"|"c"|"e" ("m" has channel counts that are not multiples of 8 and is not supported yet).
+/* size: "t"|"s"|"c"|"e" as the reference defines them (detection/yolov9.py:461-464), or "t@16"|"m@16": the zero-padded
+ * equivalents of t and m (every width a multiple of 16; same function) whose weights the host produces from the
+ * reference's by scattering them into the padded layout (clearcam_b200/detection/padding.py `pad_state_dict`).  Literal
+ * "m" is not accepted by the plan builder (widths 60/90/184 break the 16-byte slice alignment); literal "t" runs with its
+ * 24-channel convs on the generic CUDA-core kernel.
  * Weights: n host fp32 tensors in PyTorch layout, named with the reference's state-dict keys with `.list.`
  * elided, e.g. "model.0.conv.weight", "model.2.cv2.0.cv1.conv.bias", "model.22.cv2.0.2.weight"
  * (what safe_load/load_state_dict consume at detection/yolov9.py:372-373).  They are repacked to the kernel
