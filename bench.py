@@ -134,9 +134,9 @@ def run_reference(args):
     batch = 4   # measured: 4 frames per call is the fastest per-frame configuration of the torch-CPU oracle
     fr = o.synthetic_frames(batch, HW, HW, seed=1)
     pick_cpu_threads(P, fr)
-    for _ in range(max(1, min(args.warmup, 1))):
+    for _ in range(max(1, min(args.warmup, 3))):
         o.detect(SIZE, P, fr, RES)
-    steps = max(1, min(args.steps, 8))
+    steps = max(1, min(args.steps, 12))
     t0 = time.time()
     for _ in range(steps):
         o.detect(SIZE, P, fr, RES)
