@@ -34,8 +34,9 @@ class CameraBatch:
         """model: a clearcam_b200 YOLOv9 (anything with detect_batch(frames[B,H,W,3]) -> (B,300,6))."""
         self.model, self.max_age = model, max_age
         self.cams: Dict[Hashable, _Camera] = {}
-        self._stage: Dict[tuple, tuple] = {}                   # (H,W,dtype,n) -> (pinned frames, pinned rows)
+        self._stage: Dict[tuple, tuple] = {}                   # (H,W,dtype,n) -> (device frame batch, pinned rows)
         self._pin = torch.cuda.is_available()
+        self._seen: Dict[Hashable, int] = {}                   # last frame_num taken from each camera's mailbox
 
     # -- camera set (clearcam.py:207-240 init_cam; settings threshold :584, class filter :586)
     def add_camera(self, name, thresh: float = 0.5, classes=None):
@@ -54,9 +55,11 @@ class CameraBatch:
         for name, f in frames.items():
             if f is None:
                 continue
-            if f.ndim != 3 or f.shape[2] != 3 or f.dtype not in (np.uint8, np.float32):
-                raise ValueError(f"camera {name!r}: frame must be HWC BGR uint8 or float32, got {f.dtype} {f.shape}")
-            groups.setdefault((f.shape[0], f.shape[1], f.dtype.str), []).append(name)
+            dt = {torch.uint8: "|u1", torch.float32: "<f4"}.get(f.dtype) if isinstance(f, torch.Tensor) else \
+                (f.dtype.str if f.dtype in (np.uint8, np.float32) else None)
+            if f.ndim != 3 or f.shape[2] != 3 or dt is None:
+                raise ValueError(f"camera {name!r}: frame must be HWC BGR uint8 or float32, got {f.dtype} {tuple(f.shape)}")
+            groups.setdefault((int(f.shape[0]), int(f.shape[1]), dt), []).append(name)
         return groups
 
     def _buffers(self, key, n):
@@ -64,25 +67,37 @@ class CameraBatch:
         if k not in self._stage:
             H, W, dt = key
             tdt = torch.uint8 if np.dtype(dt) == np.uint8 else torch.float32
-            self._stage[k] = (torch.empty((n, H, W, 3), dtype=tdt, pin_memory=self._pin),
+            dev = "cuda" if self._pin else "cpu"
+            self._stage[k] = (torch.empty((n, H, W, 3), dtype=tdt, device=dev),
                               torch.empty((n, 300, 6), dtype=torch.float32, pin_memory=self._pin))
         return self._stage[k]
 
     def detect(self, frames: Dict[Hashable, np.ndarray]) -> Dict[Hashable, np.ndarray]:
-        """Detector only: {camera: HWC frame} -> {camera: (300,6) rows}.  One batched call per distinct frame shape."""
+        """Detector only: {camera: HWC frame} -> {camera: (300,6) rows}.  One batched call per distinct frame shape.
+        Each frame goes host -> its row of the device batch directly (asynchronously when it lives in pinned memory, e.g. a
+        FrameMailbox slot): no host-side stacking copy."""
         pending = []
         for key, names in self.group_by_shape(frames).items():
-            stage, rows = self._buffers(key, len(names))
-            view = stage.numpy()
+            dev, rows = self._buffers(key, len(names))
             for i, name in enumerate(names):
-                np.copyto(view[i], frames[name])
-            dev = stage.to("cuda", non_blocking=True) if self._pin else stage
+                f = frames[name]
+                dev[i].copy_(f if isinstance(f, torch.Tensor) else torch.from_numpy(f), non_blocking=True)
             out = self.model.detect_batch(dev)
             rows.copy_(out, non_blocking=True)
             pending.append((names, rows))
         if self._pin:
             torch.cuda.current_stream().synchronize()
         return {name: rows[i].numpy().copy() for names, rows in pending for i, name in enumerate(names)}
+
+    def step_mailboxes(self, mailboxes: Dict[Hashable, "FrameMailbox"]) -> Dict[Hashable, CameraResult]:
+        """`step` on every camera whose mailbox (clearcam_b200.ingest) holds a frame this object has not seen yet —
+        the reference's `if frame_num == last_frame_num: return` per camera (clearcam.py:446)."""
+        frames = {}
+        for name, mb in mailboxes.items():
+            got = mb.latest(self._seen.get(name, -1))
+            if got is not None:
+                self._seen[name], frames[name] = got
+        return self.step(frames) if frames else {}
 
     def step(self, frames: Dict[Hashable, np.ndarray]) -> Dict[Hashable, CameraResult]:
         for name in frames:
