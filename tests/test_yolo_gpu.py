@@ -215,3 +215,27 @@ def test_multi_camera_batch_matches_single_frame_calls():
             trk = solo.setdefault(name, ocsort.OCSort(max_age=100))
             exp = trk.update(got, 0.5)
             assert [int(t_.track_id) for t_ in exp] == [int(t_.track_id) for t_ in res[name].targets]
+
+
+def test_mailbox_ingest_feeds_the_batched_detector():
+    """rawvideo bytes -> pinned FrameMailbox slots -> CameraBatch.step_mailboxes == model(frame) per camera."""
+    import io
+    from clearcam_b200.cameras import CameraBatch
+    from clearcam_b200.ingest import FrameMailbox
+    fr, x, P = _setup("t", 320, 2, 240, 320, seed=4)
+    m = YOLOv9("t", 320, weights=P)
+    cb = CameraBatch(m)
+    boxes = {f"cam{i}": FrameMailbox(240, 320) for i in range(2)}
+    assert boxes["cam0"].latest() is None and cb.step_mailboxes(boxes) == {}
+    for i in range(2):
+        assert boxes[f"cam{i}"].fill(io.BytesIO(fr[i].numpy().tobytes()))
+    res = cb.step_mailboxes(boxes)
+    assert set(res) == {"cam0", "cam1"}
+    for i in range(2):
+        assert boxes[f"cam{i}"].latest(-1)[1].is_pinned()
+        single = m(fr[i].numpy()).numpy()
+        got = res[f"cam{i}"].rows
+        exact = np.array_equal(got, single)
+        frac, _ = _match(torch.from_numpy(single), torch.from_numpy(got))
+        assert exact or frac >= 0.9
+    assert cb.step_mailboxes(boxes) == {}                 # no new frames -> no work (clearcam.py:446)
