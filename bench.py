@@ -12,6 +12,9 @@ DFL decode -> top-300 + suppression -> scale_boxes.  Weights: seeded synthetic (
               measured live with CUDA events (cc_yolo_profile), against MEASURED_PEAKS.json bf16 peak
   cpu_baseline / --impl reference : the torch-CPU oracle (the reference's tinygrad path cannot run here) on the
               box's host cores, bounded sample.
+
+oracle/ is imported here for two things only: the CPU legs above, and — before any timed region — the seeded synthetic
+weights and frames every arm runs on (input generation).  Every timed GPU region calls clearcam_b200 alone.
 """
 import argparse
 import json

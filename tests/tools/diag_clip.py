@@ -1,6 +1,6 @@
 """GPU timing of the CLIP towers. usage: diag_clip.py [arch] [B]"""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from oracle import clip as oc
 from clearcam_b200.models.objects import OpenCLIP

@@ -1,6 +1,6 @@
 """GPU diagnostic: per-layer deviation of the CUDA path from the bf16-mirror oracle (finds where errors enter)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from oracle import yolov9 as o
 from clearcam_b200.detection.yolov9 import YOLOv9

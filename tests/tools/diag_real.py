@@ -1,6 +1,6 @@
 """Real YOLOv9-t weights + real frame: CUDA path vs fp32 oracle (and vs the reference's recorded detections)."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from oracle import yolov9 as o
 from clearcam_b200.detection.yolov9 import YOLOv9

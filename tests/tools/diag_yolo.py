@@ -1,6 +1,6 @@
 """GPU diagnostic: CUDA YOLOv9 path vs the CPU oracle (fp32 and bf16-mirror). Prints deviation statistics."""
 import sys, time, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from oracle import yolov9 as o
 from clearcam_b200.detection.yolov9 import YOLOv9

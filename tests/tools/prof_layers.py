@@ -1,6 +1,6 @@
 """Per-op device time table of one YOLOv9 forward (cc_yolo_profile). usage: prof_layers.py [size] [B] [res]"""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from oracle import yolov9 as o
 from clearcam_b200.detection.yolov9 import YOLOv9
