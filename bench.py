@@ -291,7 +291,7 @@ def main():
                 "whole_step_tflops": B * GFLOP_PER_FRAME / 1000.0 / (ms_total / K / 1000.0),
                 "per_kind_ms": {k: round(v["ms"], 4) for k, v in by.items()}}
         cpu = None
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:                  # rank 0 at N=1 only: the other ranks must not sit in a barrier
             fps, n, cores = cpu_reference_fps(P)
             cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                    "sample": f"{n} frames of the same 640x640 workload through oracle.detect (torch fp32, best of several host thread counts)"}
