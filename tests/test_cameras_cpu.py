@@ -58,3 +58,12 @@ def test_step_routes_results_to_cameras_and_tracks():
         rows = det.detect_batch(torch.from_numpy(_frames(t)["cam0"])[None])[0].numpy()
         exp = solo.update(rows, 0.5)
     np.testing.assert_array_equal(exp[0].tlwh, res["cam0"].targets[0].tlwh)
+
+
+def test_jit_infer_is_a_plain_call_keyed_by_shape():
+    from clearcam_b200.utils.helpers import jit_infer
+    cache, calls = {}, []
+    f = lambda x: calls.append(x.shape) or x.sum()          # noqa: E731
+    assert jit_infer(f, np.ones((2, 3)), cache) == 6 and jit_infer(f, np.ones((2, 3)), cache) == 6
+    assert jit_infer(f, np.ones((4, 3)), cache) == 12
+    assert set(cache) == {(2, 3), (4, 3)} and len(calls) == 3
