@@ -176,6 +176,11 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # the seeded synthetic weights are generated on the CPU by every rank: share the host cores instead of running
+        # world x all-threads on top of each other
+        torch.set_num_threads(max(1, min(16, (os.cpu_count() or 8) // world)))
+    else:
+        torch.set_num_threads(min(16, os.cpu_count() or 8))    # 16 threads serve the torch-CPU weight generation best
     from oracle import yolov9 as o
     from clearcam_b200.detection.yolov9 import YOLOv9
 

@@ -209,3 +209,29 @@ def test_zero_padded_equivalent_computes_the_same_function(size):
     assert all(v % 16 == 0 for k, v in zip("abcdefghijklmnpqrstuvw", PADDED[size]) if k not in "p")
     d, d16 = o.detect(size, P, fr, 128), o.detect(padded_size(size), P16, fr, 128)
     assert float((d - d16).abs().max()) < 1e-2
+
+
+def test_tokenizer_live_against_the_reference_on_random_text():
+    """Build container only: the reference's own tokenizer module (pure Python) side by side on generated text — mixed case,
+    digits, punctuation, apostrophe forms, runs of spaces, accented and non-Latin characters, emoji, html entities."""
+    import importlib.util
+    ref_py = "/root/reference/utils/clip_tokenizer.py"
+    if not os.path.exists(ref_py):
+        pytest.skip("reference checkout not available")
+    spec = importlib.util.spec_from_file_location("_ref_clip_tokenizer", ref_py)
+    ref = importlib.util.module_from_spec(spec)
+    try:
+        spec.loader.exec_module(ref)
+        rt = ref.SimpleTokenizer()
+    except Exception as ex:                                   # the reference module wants ftfy/regex: skip if it cannot load here
+        pytest.skip(f"reference tokenizer not importable here: {ex!r}")
+    from clearcam_b200.utils.clip_tokenizer import SimpleTokenizer
+    tok = SimpleTokenizer()
+    rng = np.random.default_rng(0)
+    words = ["person", "Ferrari", "F40", "don't", "it's", "we'll", "I'M", "dog's", "naïve", "café", "Zürich", "北京", "мотоцикл", "🚗", "😀",
+             "&amp;", "&lt;b&gt;", "3.14", "1080p", "a", "THE", "x-ray", "e-mail", "#tag", "@home", "100%", "(red)", "white/blue", "...",
+             "  ", "\t", "van", "ladder", "night-time", "ＦＵＬＬ", "ﬁre", "o'clock", "10:30", "$5", "état", "straße"]
+    for _ in range(300):
+        n = int(rng.integers(1, 9))
+        text = " ".join(words[int(i)] for i in rng.integers(0, len(words), n))
+        assert tok.encode(text) == rt.encode(text), repr(text)
