@@ -417,7 +417,8 @@ struct cc_ocsort {
               dy /= norm;
               double c = tr.vel[1] * dx + tr.vel[0] * dy;
               c = std::min(1., std::max(-1., c));
-              const double ang = (M_PI / 2.0 - std::fabs(std::acos(c))) / M_PI;
+              // c == 0 (tracks that have no direction yet) gives acos = pi/2 and an angle term of exactly 0: skip the call
+              const double ang = c == 0. ? 0. : (M_PI / 2.0 - std::fabs(std::acos(c))) / M_PI;
               const double adc = (valid * ang) * inertia * static_cast<double>(dets[d].b[4]);
               cost[static_cast<size_t>(d) * T + t] = -(iou_m[static_cast<size_t>(d) * T + t] + adc);
             }
