@@ -235,3 +235,37 @@ def test_tokenizer_live_against_the_reference_on_random_text():
         n = int(rng.integers(1, 9))
         text = " ".join(words[int(i)] for i in rng.integers(0, len(words), n))
         assert tok.encode(text) == rt.encode(text), repr(text)
+
+
+def test_reference_known_answer_156_people_tracks_on_mot16():
+    """test/run_mot.py:14-51, the reference's end-to-end check of detector + tracker: YOLOv9-t (res 960) on every frame of
+    MOT16-03.mp4 -> OCSort(max_age=60) -> 156 distinct moving person tracks.  The detections are the ORACLE's (with the
+    YOLOv9-t weights recovered from the reference's iOS blob; oracle/make_golden_mot.py), the tracker is the product's C++
+    one: the chain lands on the reference's number exactly.  (The statistic moves by +-2 % with rounding: see the script.)"""
+    from clearcam_b200.ocsort_tracker import ocsort
+    g = np.load(os.path.join(GOLD, "mot16_oracle_dets.npz"))
+    dets = g["dets"]
+    assert dets.shape == (1501, 300, 6) and int(g["expected"]) == 156
+    trk, ppl = ocsort.OCSort(max_age=60), set()
+    for pred in dets:
+        for x in trk.update(pred, 0.25):
+            if x.tracklet_len < 1 or x.speed < 2.5:
+                continue
+            if x.class_id == 0:
+                ppl.add(x.track_id)
+    assert len(ppl) == 156
+    # tie the stored detections to the oracle code where the reference's video can be read (build container only)
+    video = "/root/reference/test/videos/MOT16-03.mp4"
+    if os.path.exists(video):
+        cv2 = pytest.importorskip("cv2")
+        w = np.load(os.path.join(GOLD, "yolov9t_mot16.npz"))
+        P = {k[2:]: torch.from_numpy(w[k]) for k in w.keys() if k.startswith("w:")}
+        cap = cv2.VideoCapture(video)
+        for i in range(2):
+            ok, im = cap.read()
+            assert ok
+            with torch.no_grad():
+                pred = o.detect("t", P, torch.from_numpy(im).float()[None], 960, bgr_swap=False)[0].numpy()
+            live = dets[i][:, 4] > 0
+            assert (pred[:, 4] > 0).sum() == live.sum()
+            np.testing.assert_allclose(pred[live], dets[i][live], rtol=0, atol=2e-2)
