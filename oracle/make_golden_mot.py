@@ -5,8 +5,9 @@ person tracks with tracklet_len >= 1 and speed >= 2.5 -> the reference asserts 1
 TEST INFRASTRUCTURE.  The reference's detector cannot run here (tinygrad) and its weights are fetched from HuggingFace;
 this script runs the ORACLE detector with the YOLOv9-t weights recovered from the reference's iOS model blob
 (oracle/extract_ios_weights.py -> tests/golden/yolov9t_mot16.npz) on the reference's own video and stores the (1501,300,6)
-detections in tests/golden/mot16_oracle_dets.npz for tests/test_oracle_cpu.py.  Those blob weights take their input in the
-camera's BGR order (the same finding as for the recorded detections of test/tracks.pkl), hence bgr_swap=False.
+detections in tests/golden/mot16_oracle_dets.npz for tests/test_oracle_cpu.py.  bgr_swap=False: the configuration that also
+reproduces the detections recorded in test/tracks.pkl (the reference's fixtures were recorded by a detector
+revision without the BGR->RGB swap of detection/yolov9.py:378; either that, or the blob's first conv is stored in BGR order).
 
 Measured here: 156 people tracks = the reference's known answer.  The statistic is sensitive at the +-2 % level: the same
 chain gives 159 with the channel swap, 155 with the bf16-mirror oracle and 153 from the older-revision detections stored

@@ -240,7 +240,7 @@ def test_tokenizer_live_against_the_reference_on_random_text():
 def test_reference_known_answer_156_people_tracks_on_mot16():
     """test/run_mot.py:14-51, the reference's end-to-end check of detector + tracker: YOLOv9-t (res 960) on every frame of
     MOT16-03.mp4 -> OCSort(max_age=60) -> 156 distinct moving person tracks.  The detections are the ORACLE's (with the
-    YOLOv9-t weights recovered from the reference's iOS blob; oracle/make_golden_mot.py), the tracker is the product's C++
+    YOLOv9-t weights recovered from the reference's iOS blob, channel swap off as for test/tracks.pkl; oracle/make_golden_mot.py), the tracker is the product's C++
     one: the chain lands on the reference's number exactly.  (The statistic moves by +-2 % with rounding: see the script.)"""
     from clearcam_b200.ocsort_tracker import ocsort
     g = np.load(os.path.join(GOLD, "mot16_oracle_dets.npz"))
