@@ -6,6 +6,9 @@ from /root/reference — only possible in the build container) and stores inputs
   tests/golden/ocsort_mot16.npz     the reference's fixture test/tracks.pkl (1501 frames of (300,6) detector rows and the
                                     tracks its test/test_ocsort.py:8-14 expects), re-run through the reference here with
                                     OCSort(max_age=60), det_thresh 0.25, and checked equal to the pickle's expectation
+  tests/golden/ocsort_street.npz    the reference's unused second fixture test/tracker_inputs.pkl (1500 frames of a street
+                                    scene) through the reference with the product's settings (max_age=100, threshold 0.5)
+                                    and with the BYTE stage on
   tests/golden/ocsort_synth.npz     three seeded synthetic scenes (crossing boxes, drop-outs, low-score rows, class flips)
                                     through the reference with other constructor arguments (use_byte, max_age, delta_t)
 
@@ -104,6 +107,16 @@ def main():
                                            kw.get("delta_t", 3), kw.get("inertia", 0.2), float(kw.get("use_byte", False))])
         print(name, fr.shape, rows.shape, "ids up to", rows[:, 6].max())
     np.savez_compressed(OUT / "ocsort_synth.npz", **scenes)
+
+    # the reference's second, unused fixture: 1500 frames of recorded detections from another (street, mostly cars) video
+    real = np.stack(pickle.load(open(REF / "test" / "tracker_inputs.pkl", "rb"))).astype(np.float32)
+    out = {"frames": real}
+    for name, thr, kw in [("a", 0.5, dict(max_age=100)), ("b", 0.25, dict(max_age=30, use_byte=True))]:   # a = clearcam.py:239,584
+        rows, offs = run_reference(real, thr, **kw)
+        out[f"{name}_rows"], out[f"{name}_offsets"] = rows, offs
+        out[f"{name}_args"] = np.array([thr, kw["max_age"], float(kw.get("use_byte", False))])
+        print("tracker_inputs", name, rows.shape, "ids up to", rows[:, 6].max())
+    np.savez_compressed(OUT / "ocsort_street.npz", **out)
 
 
 if __name__ == "__main__":
