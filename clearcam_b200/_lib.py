@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libclearcam_b200.so")
+# CC_LIB: developer override used for same-box A/B runs of two builds (tools/ab.py); production loads the in-tree library
+LIB_PATH = os.environ.get("CC_LIB") or os.path.join(_HERE, "libclearcam_b200.so")
 
 
 class CCError(RuntimeError):
@@ -26,12 +27,20 @@ _SIGS = {
     "cc_conv2d": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp]),
     "cc_yolo_create": (_i, [ctypes.c_char_p, _i, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(_vp),
                             ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(_vp)]),
+    "cc_yolo_create_ex": (_i, [ctypes.c_char_p, _i, _i, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(_vp),
+                               ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(_vp)]),
     "cc_yolo_destroy": (_i, [_vp]),
     "cc_yolo_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "cc_yolo_workspace_bytes": (_i, [_vp, _i, _i, _i, _i, _i, ctypes.POINTER(ctypes.c_size_t)]),
+    "cc_yolo_set_workspace": (_i, [_vp, _vp, ctypes.c_size_t]),
+    "cc_clip_workspace_bytes": (_i, [_vp, _i, _i, ctypes.POINTER(ctypes.c_size_t)]),
+    "cc_clip_set_workspace": (_i, [_vp, _vp, ctypes.c_size_t]),
     "cc_yolo_plan_info": (_i, [_vp, _i, _i, _i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i),
                                ctypes.POINTER(_i), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     "cc_yolo_profile": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, ctypes.POINTER(_f), ctypes.POINTER(ctypes.c_double),
                              ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(_i), _vp]),
+    "cc_yolo_trace": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_char_p),
+                           ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_i), _vp]),
     "cc_yolo_layer_output": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, ctypes.POINTER(_i), ctypes.POINTER(_i),
                                   ctypes.POINTER(_i), _vp]),
     "cc_detect_postprocess": (_i, [_vp, _i, _i, _i, _f, _i, _f, _f, _f, _f, _f, _vp, _vp]),
@@ -45,6 +54,7 @@ _SIGS = {
     "cc_clip_profile": (_i, [_vp, _i, _vp, _i, _vp, _i, ctypes.POINTER(_f), ctypes.POINTER(ctypes.c_double),
                              ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(_i), ctypes.POINTER(ctypes.c_double), _vp]),
     "cc_search_scores": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp]),
+    "cc_search_topk": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "cc_clip_preprocess": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
     "cc_ocsort_create": (_i, [_i, _i, ctypes.c_double, _i, ctypes.c_double, _i, ctypes.POINTER(_vp)]),
     "cc_ocsort_destroy": (_i, [_vp]),
@@ -65,7 +75,11 @@ def lib():
                 "(there is no CPU fallback)")
         h = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in _SIGS.items():
-            fn = getattr(h, name)
+            fn = getattr(h, name, None)
+            if fn is None and os.environ.get("CC_LIB"):
+                continue              # an older build under A/B comparison may lack newer entry points
+            if fn is None:
+                raise CCError(f"{LIB_PATH} does not export {name}: rebuild it (python -c 'import __graft_entry__ as g; g.build()')")
             fn.restype = res
             fn.argtypes = args
         _lib = h

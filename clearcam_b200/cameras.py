@@ -14,6 +14,7 @@ import numpy as np
 import torch
 
 from .ocsort_tracker import ocsort
+from .utils.helpers import batch_bucket
 from .ocsort_tracker.STrack import STrack
 
 
@@ -34,9 +35,10 @@ class CameraBatch:
         """model: a clearcam_b200 YOLOv9 (anything with detect_batch(frames[B,H,W,3]) -> (B,300,6))."""
         self.model, self.max_age = model, max_age
         self.cams: Dict[Hashable, _Camera] = {}
-        self._stage: Dict[tuple, tuple] = {}                   # (H,W,dtype,n) -> (device frame batch, pinned rows)
+        self._stage: Dict[tuple, tuple] = {}                   # (H,W,dtype,bucket) -> (device frame batch, pinned rows)
         self._pin = torch.cuda.is_available()
         self._seen: Dict[Hashable, int] = {}                   # last frame_num taken from each camera's mailbox
+        self._where: Dict[Hashable, tuple] = {}                # camera -> (device batch, row) of its frame in the last detect()
 
     # -- camera set (clearcam.py:207-240 init_cam; settings threshold :584, class filter :586)
     def add_camera(self, name, thresh: float = 0.5, classes=None):
@@ -44,9 +46,14 @@ class CameraBatch:
 
     def remove_camera(self, name):
         self.cams.pop(name, None)
+        self._where.pop(name, None)
+        self._seen.pop(name, None)             # a re-added camera starts a new mailbox whose frame_num restarts at 0
 
     def reset_tracker(self, name):
         self.cams[name].tracker = ocsort.OCSort(max_age=self.max_age)
+        self._seen.pop(name, None)
+
+    bucket = staticmethod(batch_bucket)   # group sizes are padded to a small set of batch sizes (bounded plan count)
 
     # -- one pass over every camera that has a new frame
     @staticmethod
@@ -63,13 +70,13 @@ class CameraBatch:
         return groups
 
     def _buffers(self, key, n):
-        k = key + (n,)
+        k = key + (self.bucket(n),)
         if k not in self._stage:
             H, W, dt = key
             tdt = torch.uint8 if np.dtype(dt) == np.uint8 else torch.float32
             dev = "cuda" if self._pin else "cpu"
-            self._stage[k] = (torch.empty((n, H, W, 3), dtype=tdt, device=dev),
-                              torch.empty((n, 300, 6), dtype=torch.float32, pin_memory=self._pin))
+            self._stage[k] = (torch.zeros((k[-1], H, W, 3), dtype=tdt, device=dev),
+                              torch.empty((k[-1], 300, 6), dtype=torch.float32, pin_memory=self._pin))
         return self._stage[k]
 
     def detect(self, frames: Dict[Hashable, np.ndarray]) -> Dict[Hashable, np.ndarray]:
@@ -82,12 +89,19 @@ class CameraBatch:
             for i, name in enumerate(names):
                 f = frames[name]
                 dev[i].copy_(f if isinstance(f, torch.Tensor) else torch.from_numpy(f), non_blocking=True)
+                self._where[name] = (dev, i)
             out = self.model.detect_batch(dev)
             rows.copy_(out, non_blocking=True)
             pending.append((names, rows))
         if self._pin:
             torch.cuda.current_stream().synchronize()
         return {name: rows[i].numpy().copy() for names, rows in pending for i, name in enumerate(names)}
+
+    def device_frame(self, name) -> torch.Tensor:
+        """The [H,W,3] device copy of the frame camera `name` contributed to the last detect()/step() — what the object
+        crops for CLIP are cut from (ObjectFinder.embed_crops) without a second upload.  Valid until the next step."""
+        dev, i = self._where[name]
+        return dev[i]
 
     def step_mailboxes(self, mailboxes: Dict[Hashable, "FrameMailbox"]) -> Dict[Hashable, CameraResult]:
         """`step` on every camera whose mailbox (clearcam_b200.ingest) holds a frame this object has not seen yet —

@@ -28,6 +28,27 @@ PFN_encodeTiled get_encode_tiled() {
   return fn;
 }
 
+int Arena::reserve(size_t bytes) {
+  if (bytes <= cap) return CC_OK;
+  CC_REQUIRE(owned, "workspace too small: the plan needs %zu bytes, the caller-owned workspace holds %zu", bytes, cap);
+  if (base) { cudaFree(base); base = nullptr; cap = 0; }     // cudaFree synchronises: nothing in flight still reads it
+  bytes = (bytes + (size_t(1) << 21) - 1) & ~((size_t(1) << 21) - 1);
+  if (cudaMalloc(&base, bytes) != cudaSuccess) {
+    base = nullptr;
+    set_error("workspace: cudaMalloc(%zu) failed", bytes);
+    return CC_ERR_CUDA;
+  }
+  cap = bytes;
+  ++gen;
+  return CC_OK;
+}
+int Arena::adopt(void* d_ws, size_t bytes) {
+  if (owned && base) cudaFree(base);
+  base = d_ws; cap = d_ws ? bytes : 0; owned = d_ws == nullptr;
+  ++gen;
+  return CC_OK;
+}
+
 int device_sm_count() {
   static int n = -2;
   if (n == -2) {

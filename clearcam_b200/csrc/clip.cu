@@ -45,10 +45,9 @@ struct VOp {
 struct ClipPlan {
   int B = 0; bool text = false;
   std::vector<VOp> ops;
-  std::vector<void*> allocs;
-  size_t alloc_bytes = 0;
+  size_t alloc_bytes = 0;      // bytes of the handle's shared workspace this plan addresses
+  uint64_t gen = 0, last_use = 0;
   double flops = 0;
-  ~ClipPlan() { for (void* p : allocs) cudaFree(p); }
 };
 
 struct ClipModel {
@@ -65,7 +64,9 @@ struct ClipModel {
   // text tower
   float *tok = nullptr, *pos_t = nullptr, *lnf_g = nullptr, *lnf_b = nullptr;
   __nv_bfloat16* tprojT = nullptr;
-  std::map<std::string, std::unique_ptr<ClipPlan>> plans;
+  std::map<std::string, std::unique_ptr<ClipPlan>> plans;   // bounded, least recently used goes first
+  Arena arena;                 // activation workspace shared by all plans (size of the largest)
+  uint64_t tick = 0;
   ~ClipModel() { plans.clear(); for (void* p : allocs) cudaFree(p); }
 
   int get(const std::string& name, long long n, const float** out) {
@@ -125,12 +126,12 @@ struct ClipModel {
 
 struct PlanBuilder {
   ClipModel& M; ClipPlan& P; int rc = CC_OK;
+  Bump bump;                   // workspace carving; bump.dry = measuring pass (descriptors are not built)
   PlanBuilder(ClipModel& m, ClipPlan& p) : M(m), P(p) {}
   void* dalloc(size_t bytes) {
     if (rc) return nullptr;
-    void* d = nullptr;
-    if (cudaMalloc(&d, bytes) != cudaSuccess) { set_error("clip plan: cudaMalloc(%zu) failed", bytes); rc = CC_ERR_CUDA; return nullptr; }
-    P.allocs.push_back(d); P.alloc_bytes += bytes;
+    void* d = bump.take(bytes);
+    P.alloc_bytes = bump.off;
     return d;
   }
   // out[M,N] = act(A[M,K] . Wt[N,K]^T + bias) (+res)
@@ -143,6 +144,7 @@ struct PlanBuilder {
     d.k = 1; d.stride = 1; d.w = Wt; d.bias = bias;
     d.out = out; d.out_cs = ldc; d.out_co = 0; d.Cout = N; d.out_f32 = f32 ? 1 : 0; d.act = act;
     d.res = res; d.res_cs = ldc; d.res_co = 0; d.out_ns = out_ns;
+    if (bump.dry) return;
     VOp op; op.kind = VOp::GEMM; op.name = name;
     rc = conv_gemm_build(d, M.sms, &op.gemm);
     if (rc) return;
@@ -280,19 +282,63 @@ int cc_clip_destroy(cc_clip* h) {
   return CC_OK;
 }
 
-static int clip_plan(cc_clip* h, bool text, int B, ClipPlan** out) {
-  const std::string key = std::string(text ? "t" : "i") + std::to_string(B);
-  auto it = h->m.plans.find(key);
-  if (it == h->m.plans.end()) {
-    std::unique_ptr<ClipPlan> P(new ClipPlan());
-    P->B = B; P->text = text;
-    PlanBuilder b(h->m, *P);
-    int rc = text ? b.build_text(B) : b.build_image(B);
-    if (rc) return rc;
-    it = h->m.plans.emplace(key, std::move(P)).first;
-  }
-  *out = it->second.get();
+static constexpr size_t kMaxClipPlans = 16;
+
+static int clip_plan_bytes(cc_clip* h, bool text, int B, size_t* bytes) {
+  ClipPlan tmp;
+  tmp.B = B; tmp.text = text;
+  PlanBuilder dry(h->m, tmp);
+  dry.bump.dry = true;
+  int rc = text ? dry.build_text(B) : dry.build_image(B);
+  if (rc) return rc;
+  *bytes = dry.bump.off + 1024;
   return CC_OK;
+}
+static int clip_plan(cc_clip* h, bool text, int B, ClipPlan** out) {
+  ClipModel& M = h->m;
+  const std::string key = std::string(text ? "t" : "i") + std::to_string(B);
+  auto it = M.plans.find(key);
+  if (it != M.plans.end() && it->second->gen == M.arena.gen) {
+    it->second->last_use = ++M.tick;
+    *out = it->second.get();
+    return CC_OK;
+  }
+  size_t bytes = 0;
+  int rc = clip_plan_bytes(h, text, B, &bytes);
+  if (rc) return rc;
+  if ((rc = M.arena.reserve(bytes))) return rc;
+  for (auto p = M.plans.begin(); p != M.plans.end();)
+    p = (p->second->gen != M.arena.gen) ? M.plans.erase(p) : std::next(p);
+  std::unique_ptr<ClipPlan> P(new ClipPlan());
+  P->B = B; P->text = text;
+  PlanBuilder b(M, *P);
+  b.bump.base = static_cast<uint8_t*>(M.arena.base);
+  rc = text ? b.build_text(B) : b.build_image(B);
+  if (rc) return rc;
+  CC_REQUIRE(b.bump.off <= M.arena.cap, "clip plan: workspace overrun (%zu > %zu)", b.bump.off, M.arena.cap);
+  P->gen = M.arena.gen;
+  P->last_use = ++M.tick;
+  if (M.plans.size() >= kMaxClipPlans) {
+    auto lru = M.plans.begin();
+    for (auto p = M.plans.begin(); p != M.plans.end(); ++p)
+      if (p->second->last_use < lru->second->last_use) lru = p;
+    M.plans.erase(lru);
+  }
+  *out = (M.plans[key] = std::move(P)).get();
+  return CC_OK;
+}
+
+int cc_clip_workspace_bytes(cc_clip* h, int text, int B, size_t* bytes) {
+  CC_REQUIRE(h && bytes && B > 0, "cc_clip_workspace_bytes: bad argument");
+  return clip_plan_bytes(h, text != 0, B, bytes);
+}
+
+int cc_clip_set_workspace(cc_clip* h, void* d_workspace, size_t bytes) {
+  CC_REQUIRE(h, "cc_clip_set_workspace: null handle");
+  CC_REQUIRE(d_workspace == nullptr || (reinterpret_cast<uintptr_t>(d_workspace) & 255) == 0,
+             "cc_clip_set_workspace: the workspace must be 256-byte aligned");
+  h->m.plans.clear();
+  return h->m.arena.adopt(d_workspace, bytes);
 }
 
 int cc_clip_encode_image(cc_clip* h, const float* d_x, int B, float* d_out, long long out_row_stride, void* stream) {
@@ -341,6 +387,14 @@ int cc_clip_profile(cc_clip* h, int text, const void* d_in, int B, float* d_out,
 int cc_search_scores(const float* d_index, int N, int D, const float* d_q, int Q, float* d_scores, void* stream) {
   CC_REQUIRE(d_index && d_q && d_scores && N >= 0 && D > 0 && Q > 0, "cc_search_scores: bad argument");
   return search_scores_launch(d_index, d_q, d_scores, N, D, Q, static_cast<cudaStream_t>(stream));
+}
+
+int cc_search_topk(const float* d_index, int N, int D, const float* d_q, const int32_t* d_group, const uint8_t* d_mask, int G, int k,
+                   void* d_workspace, int32_t* d_rows, float* d_scores, void* stream) {
+  CC_REQUIRE(d_index && d_q && d_group && d_workspace && d_rows && d_scores && N >= 0 && D > 0 && G >= 0 && k > 0,
+             "cc_search_topk: bad argument");
+  return search_topk_launch(d_index, d_q, d_group, d_mask, static_cast<unsigned long long*>(d_workspace), N, D, G, k, d_rows, d_scores,
+                            static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

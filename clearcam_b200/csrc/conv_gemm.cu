@@ -26,7 +26,7 @@ namespace cc {
 #endif
 static constexpr int kEpiThreads = 32 * CC_EPI_WARPS;   // epilogue warps (multiple of 4: one per TMEM lane quarter)
 static constexpr int kThreads = 128 + kEpiThreads;      // w0 TMA, w1 MMA, w2 TMEM alloc, w3 idle, w4.. epilogue
-static constexpr int kColGroups = CC_EPI_WARPS / 4;     // warps sharing a lane quarter split the 16-column chunks
+static constexpr int kMaxAcc = 4;                       // TMEM accumulator slots == independent epilogue groups (2 or 4)
 static constexpr int kTileM = 128;
 static constexpr uint32_t kTmemCols = 512;
 static constexpr int kMaxSmem = 232448;  // 227 KB
@@ -117,6 +117,8 @@ __device__ __forceinline__ void mma_issuer(const GemmParams& p, uint8_t* sA, uin
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    const int n_acc = p.n_acc;
+    const uint32_t acc_cols = kTmemCols / n_acc;
     if (BRES) { mbar_wait(bres_bar, 0); tc_fence_after(); }
     if (p.halo) {
       int sa = 0;
@@ -127,7 +129,7 @@ __device__ __forceinline__ void mma_issuer(const GemmParams& p, uint8_t* sA, uin
       for (int tile = blockIdx.x; tile < num_tiles; tile += tstride) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * 256;
+        const uint32_t d_tmem = tmem_base + acc * acc_cols;
         for (int ch = 0; ch < cpt; ++ch) {
           mbar_wait(&afull_bar[sa], pa);
           tc_fence_after();
@@ -164,28 +166,54 @@ __device__ __forceinline__ void mma_issuer(const GemmParams& p, uint8_t* sA, uin
           }
           if (++sa == hstages) { sa = 0; pa ^= 1; }
         }
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        if (++acc == n_acc) { acc = 0; acc_phase ^= 1; }
       }
     } else {
+      const bool whole_tile = BRES && num_kb <= 4 && num_kb <= S && !(p.dbg & 8);
       for (int tile = blockIdx.x; tile < num_tiles; tile += tstride) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * 256;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+        const uint32_t d_tmem = tmem_base + acc * acc_cols;
+        if (whole_tile) {
+          // small-K tile with resident weights (1x1 convs, K <= 256): wait for all its activation stages, then issue the
+          // whole tile under ONE elect block (an elect block costs the warp ~300 cycles, more than the MMAs of a k-block)
+          int s2 = stage;
+          uint32_t ph2 = phase;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&full_bar[s2], ph2);
+            if (++s2 == S) { s2 = 0; ph2 ^= 1; }
+          }
           tc_fence_after();
           if (elect_one()) {
-            mma_kblock<KPB>(d_tmem, d_tile | (sA16 + stage * a16), d_tile | (sB16 + (BRES ? kb : stage) * b16), idesc,
-                            static_cast<uint32_t>(kb != 0));
-            umma_commit(&empty_bar[stage]);                         // frees this smem stage once the MMAs have read it
-            if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);     // accumulator complete -> epilogue
+            int s3 = stage;
+#pragma unroll
+            for (int kb = 0; kb < 4; ++kb) {
+              if (kb < num_kb) {
+                mma_kblock<KPB>(d_tmem, d_tile | (sA16 + s3 * a16), d_tile | (sB16 + kb * b16), idesc, static_cast<uint32_t>(kb != 0));
+                umma_commit(&empty_bar[s3]);
+                if (++s3 == S) s3 = 0;
+              }
+            }
+            umma_commit(&tfull_bar[acc]);
           }
           __syncwarp();
-          if (++stage == S) { stage = 0; phase ^= 1; }
+          stage = s2;
+          phase = ph2;
+        } else {
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            if (elect_one()) {
+              mma_kblock<KPB>(d_tmem, d_tile | (sA16 + stage * a16), d_tile | (sB16 + (BRES ? kb : stage) * b16), idesc,
+                              static_cast<uint32_t>(kb != 0));
+              umma_commit(&empty_bar[stage]);                         // frees this smem stage once the MMAs have read it
+              if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);     // accumulator complete -> epilogue
+            }
+            __syncwarp();
+            if (++stage == S) { stage = 0; phase ^= 1; }
+          }
         }
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        if (++acc == n_acc) { acc = 0; acc_phase ^= 1; }
       }
     }
 }
@@ -204,28 +232,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   const uint32_t b_bytes = p.BN * row_bytes;
   const int S = p.stages;
   constexpr int es = F32 ? 4 : 2;
-  const int CH = F32 ? (p.BN < 64 ? p.BN : 64) : (p.BN < 128 ? p.BN : 128);  // columns per staging pass
+  const int NG = p.n_acc;                                              // epilogue groups == TMEM accumulator slots (2 or 4)
+  const int CH = p.CH;                                                 // columns per staging pass
   const uint32_t pitch = p.tma_store ? CH * es : CH * es + 16;
-  const uint32_t stg_bytes = (kTileM * pitch + 15) & ~15u;           // one staging buffer
+  const uint32_t stg_bytes = (kTileM * pitch + 15) & ~15u;           // one staging buffer per epilogue group
 
   const uint32_t a_region = p.halo ? p.halo_stages * p.halo_bytes : S * a_bytes;   // halo mode: S = B stages
   uint8_t* sA = smem;
   uint8_t* sB = sA + a_region;
   const int num_kb_all = p.num_taps * p.chunks_per_tap;
   // resident-B mode: sB holds ALL k-blocks of the weights (loaded once); the ring then carries A only
-  uint8_t* sStage = sB + (p.b_res ? num_kb_all : S) * b_bytes;
-  float* sBias = reinterpret_cast<float*>(sStage + stg_bytes * (p.tma_store ? p.stg_bufs : 1));
+  uint8_t* sStage = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(sB + (p.b_res ? num_kb_all : S) * b_bytes) + 1023) & ~uintptr_t(1023));
+  float* sBias = reinterpret_cast<float*>(sStage + stg_bytes * NG);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + p.cout);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + S;
-  uint64_t* tfull_bar = bars + 2 * S;
-  uint64_t* tempty_bar = bars + 2 * S + 2;
-  uint64_t* afull_bar = bars + 2 * S + 4;     // halo mode (up to 4 stages)
-  uint64_t* aempty_bar = bars + 2 * S + 8;
-  uint64_t* bres_bar = bars + 2 * S + 12;     // resident-B mode
-  uint64_t* res_bar = bars + 2 * S + 13;      // residual prefetch (one per staging buffer)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 15);
+  uint64_t* tfull_bar = bars + 2 * S;           // [kMaxAcc]
+  uint64_t* tempty_bar = bars + 2 * S + 4;      // [kMaxAcc]
+  uint64_t* afull_bar = bars + 2 * S + 8;       // halo mode (up to 4 stages)
+  uint64_t* aempty_bar = bars + 2 * S + 12;
+  uint64_t* bres_bar = bars + 2 * S + 16;       // resident-B mode
+  uint64_t* res_bar = bars + 2 * S + 17;        // residual prefetch (one per epilogue group)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 21);
 
+  if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[0] = globaltimer_ns();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
@@ -236,17 +267,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kMaxAcc; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], p.epi_threads >> 5);   // one arrival per epilogue warp
-    }
-    for (int i = 0; i < 4; ++i) {
+      mbar_init(&tempty_bar[i], 1 << p.lgw);          // one arrival per warp of the group that owns the slot
       mbar_init(&afull_bar[i], 1);
       mbar_init(&aempty_bar[i], 1);
+      mbar_init(&res_bar[i], 1);
     }
     mbar_init(bres_bar, 1);
-    mbar_init(&res_bar[0], 1);
-    mbar_init(&res_bar[1], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -278,6 +306,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         for (int kb = 0; kb < num_kb_all; ++kb) tma_load_2d(sB + kb * b_bytes, &p.tmB, bres_bar, kb * p.BK, 0);
       }
       pdl_wait();
+      if (p.trace && blockIdx.x == 0) p.trace[1] = globaltimer_ns();
       if (p.halo) {
         int sa = 0;
         uint32_t pa = 0;
@@ -289,17 +318,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             mbar_wait(&aempty_bar[sa], pa ^ 1);
             if (p.dbg & 4) mbar_arrive(&afull_bar[sa]);
             else {
-            mbar_arrive_expect_tx(&afull_bar[sa], p.halo_bytes);
-            tma_load_5d(sA + sa * p.halo_bytes, &p.tmA, &afull_bar[sa], ch * p.BK, w0 - 1, n0, h0 - 1, 0);
+              mbar_arrive_expect_tx(&afull_bar[sa], p.halo_bytes);
+              tma_load_5d(sA + sa * p.halo_bytes, &p.tmA, &afull_bar[sa], ch * p.BK, w0 - 1, n0, h0 - 1, 0);
             }
             if (++sa == p.halo_stages) { sa = 0; pa ^= 1; }
             if (!p.b_res)
-            for (int t = 0; t < 9; ++t) {
-              mbar_wait(&empty_bar[stage], phase ^ 1);
-              mbar_arrive_expect_tx(&full_bar[stage], b_bytes);
-              tma_load_2d(sB + stage * b_bytes, &p.tmB, &full_bar[stage], t * cin + ch * p.BK, nb * p.BN);
-              if (++stage == S) { stage = 0; phase ^= 1; }
-            }
+              for (int t = 0; t < 9; ++t) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                mbar_arrive_expect_tx(&full_bar[stage], b_bytes);
+                tma_load_2d(sB + stage * b_bytes, &p.tmB, &full_bar[stage], t * cin + ch * p.BK, nb * p.BN);
+                if (++stage == S) { stage = 0; phase ^= 1; }
+              }
           }
         }
       } else
@@ -317,7 +346,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             mbar_wait(&empty_bar[stage], phase ^ 1);
             mbar_arrive_expect_tx(&full_bar[stage], (p.dbg & 4) ? (p.b_res ? 0 : b_bytes) : (p.b_res ? a_bytes : a_bytes + b_bytes));
             if (!(p.dbg & 4))
-            tma_load_5d(sA + stage * a_bytes, &p.tmA, &full_bar[stage], c_base + ch * p.BK, c1, c2, c3, c4);
+              tma_load_5d(sA + stage * a_bytes, &p.tmA, &full_bar[stage], c_base + ch * p.BK, c1, c2, c3, c4);
             if (!p.b_res) tma_load_2d(sB + stage * b_bytes, &p.tmB, &full_bar[stage], kb * p.BK, nb * p.BN);
             if (++stage == S) { stage = 0; phase ^= 1; }
           }
@@ -333,49 +362,58 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     else if (p.BK == 32) CC_ISSUE(2);
     else CC_ISSUE(1);
 #undef CC_ISSUE
-  } else if (warp >= 4 && warp < 4 + (p.epi_threads >> 5)) {
-    // (narrow tiles: warps without a 16-column chunk to convert sit the kernel out instead of paying the per-tile
-    //  bookkeeping and barriers)
-    // ===================== epilogue: 8 warps; warps q and q+4 share TMEM lane quarter q and split the
-    // 16-column chunks between them (even / odd); thread == output row in the register phase ============
+  } else if (warp >= 4 && warp < 4 + (NG << p.lgw)) {
+    // ===================== epilogue: NG independent groups of 4 or 8 warps.  Group g owns TMEM accumulator slot g, its own
+    // staging buffer, named barrier and residual barrier, and handles every NG-th tile of this CTA, so up to NG tile
+    // epilogues are in flight at once.  (One 16-warp epilogue per tile was a serial chain of ~2500 cycles — tfull wait,
+    // staging-free barrier, tcgen05.ld, activation, st.shared, proxy fence, barrier, TMA store — which set the tile rate of
+    // every small-K layer: 1.3-1.4 us per tile whatever the tile did, profiles/r02_issue_loop.md.)  Inside a group the
+    // warp's TMEM lane quarter is warp & 3; with 8-warp groups (wide tiles) the two warps of a lane quarter split the
+    // 16-column chunks of a pass.  thread == output row in the register phase. ============
+    const int lgw = p.lgw;                     // log2(warps per group): 2 or 3
+    const int grp = (warp - 4) >> lgw;
+    const int wig = (warp - 4) & ((1 << lgw) - 1);
+    const int gthreads = 32 << lgw;
+    const int gt = static_cast<int>(threadIdx.x) - 128 - grp * gthreads;   // thread within the group
     const int ew = warp & 3;                   // TMEM lane quarter this warp may access
-    const int half = (warp - 4) >> 2;          // which 16-column chunks of a pass this warp converts (mod kColGroups)
+    const int half = wig >> 2;                 // which 16-column chunks of a pass this warp converts
     const int row = ew * 32 + lane;            // row of the 128-pixel tile
-    const int et = threadIdx.x - 128;          // 0..kEpiThreads-1
+    const int cstep = 16 << (lgw - 2);         // column stride between the chunks one warp converts
+    const uint32_t bar_id = 1 + grp;
+    uint8_t* const sbuf = sStage + grp * stg_bytes;
+    uint64_t* const rbar = &res_bar[grp];
     const int TWm = (1 << p.lTW) - 1, THm = (1 << p.lTH) - 1;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    uint32_t pass_ctr = 0;   // staging passes issued so far (TMA-store double buffering)
+    const uint32_t t_row = tmem_base + grp * (kTmemCols / NG) + (static_cast<uint32_t>(ew * 32) << 16);
+    uint32_t tcount = 0;     // tiles this group has taken -> phase of its accumulator barriers
+    uint32_t pass_ctr = 0;   // staging passes of this group so far
     const int passes_per_tile = (p.BN + CH - 1) / CH;
-    const int cstep = (p.epi_threads >> 7) * 16;   // column stride between the chunks one warp converts
     // TMA-store staging: rows of 128 B (SWIZZLE_128B: 16-B chunk j of row r at slot j ^ (r & 7)) or, for tiles whose
     // pass is an odd multiple of 64 B, rows of 64 B (SWIZZLE_64B: slot j ^ ((r >> 1) & 3)); sub-tiles of 128 rows follow
     // each other
     const int lrow = p.stg_lrow, srow = 1 << lrow;
     const uint32_t swz = lrow == 7 ? (row & 7) : ((row >> 1) & 3);
-    // residual prefetch (in-place residual through tmC): the TMA load of the residual sub-tiles of staging pass `k`
-    // lands in the buffer the pass will overwrite with its result; issued one pass ahead by thread et == 0
+    // residual prefetch (in-place residual through tmC): the TMA load of the residual sub-tiles of this group's staging
+    // pass `k` lands in the buffer the pass will overwrite with its result; issued by thread gt == 0 as soon as the
+    // previous store has read the buffer
     auto issue_res = [&](uint32_t k) {
-      const int t_idx = static_cast<int>(k) / passes_per_tile;                       // k-th pass of this CTA
-      const int tile_k = blockIdx.x + t_idx * gridDim.x;
+      const int jg = static_cast<int>(k) / passes_per_tile;                          // k-th pass of this group
+      const int tile_k = blockIdx.x + (grp + jg * NG) * gridDim.x;
       if (tile_k >= p.num_tiles) return;
-      const int cc0k = (static_cast<int>(k) - t_idx * passes_per_tile) * CH;
+      const int cc0k = (static_cast<int>(k) - jg * passes_per_tile) * CH;
       const int chnk = (p.BN - cc0k) < CH ? (p.BN - cc0k) : CH;
       const TileXY tk = tile_origin(p, tile_k, p.lTW);
       const int nbk = tk.nb, w0k = tk.w0, h0k = tk.h0, n0k = tk.n0;
-      const int b = (p.stg_bufs == 2) ? (k & 1) : 0;
-      uint8_t* dstb = sStage + b * stg_bytes;
       const int nsub = (chnk * es) >> lrow;
-      mbar_arrive_expect_tx(&res_bar[b], nsub * (kTileM << lrow));
+      mbar_arrive_expect_tx(rbar, nsub * (kTileM << lrow));
       for (int j = 0; j < nsub; ++j) {
         const int cc = nbk * p.BN + cc0k + j * (srow / es);
-        if (p.halo) tma_load_5d(dstb + j * (kTileM << lrow), &p.tmC, &res_bar[b], cc, w0k, n0k, h0k, 0);
-        else tma_load_5d(dstb + j * (kTileM << lrow), &p.tmC, &res_bar[b], cc, w0k, h0k, n0k, 0);
+        if (p.halo) tma_load_5d(sbuf + j * (kTileM << lrow), &p.tmC, rbar, cc, w0k, n0k, h0k, 0);
+        else tma_load_5d(sbuf + j * (kTileM << lrow), &p.tmC, rbar, cc, w0k, h0k, n0k, 0);
       }
     };
     pdl_wait();   // residual reads below depend on the previous kernel's output
-    if (p.res_tma == 1 && et == 0) issue_res(0);
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    if (p.res_tma == 1 && gt == 0) issue_res(0);
+    for (int tile = blockIdx.x + grp * gridDim.x; tile < p.num_tiles; tile += NG * gridDim.x, ++tcount) {
       const TileXY tx = tile_origin(p, tile, p.lTW);
       const int nb = tx.nb, w0 = tx.w0, h0 = tx.h0, n0 = tx.n0;
 
@@ -386,34 +424,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       const bool pvalid = (pw < p.W) && (ph < p.H) && (pn < p.N);
       const long long ppix = static_cast<long long>(pn) * p.out_ns + ph * p.W + pw;
 
-      mbar_wait(&tfull_bar[acc], acc_phase);
+      mbar_wait(&tfull_bar[grp], tcount & 1);
       tc_fence_after();
       if (p.dbg & 1) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        if (lane == 0) mbar_arrive(&tempty_bar[grp]);
         continue;
       }
-      const uint32_t t_row = tmem_base + acc * 256 + (static_cast<uint32_t>(ew * 32) << 16);
 
       for (int cc0 = 0; cc0 < p.BN; cc0 += CH) {
         const int chn = (p.BN - cc0) < CH ? (p.BN - cc0) : CH;  // columns in this pass (multiple of 16)
-        uint8_t* sbuf = sStage;
-        if (p.tma_store) {
-          if (p.stg_bufs == 2) sbuf += (pass_ctr & 1) * stg_bytes;
-          if (et == 0 && p.res_tma != 1) {  // the buffer about to be overwritten must have been read by its TMA store
-            if (p.stg_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
-          }
-        }
         if (p.res_tma == 1) {
-          // the residual tile has landed in this buffer (which also proves the buffer was free)
-          const uint32_t b = (p.stg_bufs == 2) ? (pass_ctr & 1) : 0;
-          const uint32_t par = (p.stg_bufs == 2) ? ((pass_ctr >> 1) & 1) : (pass_ctr & 1);
-          mbar_wait(&res_bar[b], par);
+          // the residual tile has landed in the staging buffer (which also proves the buffer was free)
+          mbar_wait(rbar, pass_ctr & 1);
         } else {
-          named_bar_sync(1, p.epi_threads);                        // staging buffer free
+          if (p.tma_store && gt == 0) tma_store_wait_read<0>();   // the previous store of this group has read the buffer
+          named_bar_sync(bar_id, gthreads);                        // staging buffer free
         }
         for (int c = half * 16; c < chn; c += cstep) {
           uint32_t v[16];
@@ -495,32 +522,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                                pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
             }
           } else {
-          uint8_t* dst = sStage + row * pitch + c * es;
-          if (F32) {
+            uint8_t* dst = sbuf + row * pitch + c * es;
+            if (F32) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<float4*>(dst + 16 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          } else {
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<float4*>(dst + 16 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            } else {
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
-              *reinterpret_cast<uint4*>(dst + 16 * j) =
-                  make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                             pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
-          }
+              for (int j = 0; j < 2; ++j)
+                *reinterpret_cast<uint4*>(dst + 16 * j) =
+                    make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                               pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+            }
           }
         }
         if (cc0 + CH >= p.BN) {
-          // all TMEM reads of this accumulator done -> hand it back to the MMA warp.  ONE arrival per warp: 512 threads
-          // arriving on the same mbarrier serialise in the LSU (~2.5k cycles per tile, the floor of every small layer
-          // before this change; CC_DBG bisection, profiles/r02)
+          // all TMEM reads of this accumulator done -> hand it back to the MMA warp.  ONE arrival per warp: hundreds of
+          // threads arriving on the same mbarrier serialise in the LSU (CC_DBG bisection, profiles/r02)
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          if (lane == 0) mbar_arrive(&tempty_bar[grp]);
         }
         if (p.tma_store) {
-          fence_proxy_async_smem();        // generic-proxy smem writes -> visible to the TMA (async proxy)
-          named_bar_sync(1, p.epi_threads);  // staging filled
-          if (et == 0) {
+          fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the TMA (async proxy)
+          named_bar_sync(bar_id, gthreads);  // staging filled
+          if (gt == 0) {
             const int nsub = (chn * es) >> lrow;
             const int col0 = nb * p.BN + cc0;
             for (int j = 0; j < nsub; ++j) {
@@ -533,46 +559,45 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             }
             tma_store_commit();
             if (p.res_tma == 1) {
-              // next pass's buffer: with two buffers its last store is one group older than the one just committed
-              if (p.stg_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+              tma_store_wait_read<0>();      // the buffer is free again once the store has read it
               issue_res(pass_ctr + 1);
             }
           }
           ++pass_ctr;
           continue;
         }
-        named_bar_sync(1, p.epi_threads);  // staging filled
-        // coalesced copy-out, division free: a group of `gsz` (power of two >= chunks per row) lanes owns one row
+        named_bar_sync(bar_id, gthreads);  // staging filled
+        // coalesced copy-out, division free: a set of `1 << lg` (power of two >= chunks per row) lanes owns one row
         const int cpr = (chn * es) >> 4;  // 16-B chunks per row (2..16)
         const int lg = cpr > 8 ? 4 : (cpr > 4 ? 3 : (cpr > 2 ? 2 : 1));
-        const int chk = et & ((1 << lg) - 1);
-        const int rstep = p.epi_threads >> lg;
+        const int chk = gt & ((1 << lg) - 1);
+        const int rstep = gthreads >> lg;
         if (chk < cpr) {
           uint8_t* gbase = reinterpret_cast<uint8_t*>(p.out) + static_cast<size_t>(p.out_co + nb * p.BN + cc0) * es + chk * 16;
-          for (int r = et >> lg; r < kTileM; r += rstep) {
+          for (int r = gt >> lg; r < kTileM; r += rstep) {
             int qw, qh, qn;
             if (p.halo) { qw = w0 + (r & 7); qn = n0 + ((r >> 3) & ((1 << p.lTN) - 1)); qh = h0 + (r >> (3 + p.lTN)); }
             else { qw = w0 + (r & TWm); qh = h0 + ((r >> p.lTW) & THm); qn = n0 + (r >> (p.lTW + p.lTH)); }
             if (qw < p.W && qh < p.H && qn < p.N) {
               const long long pix = static_cast<long long>(qn) * p.out_ns + qh * p.W + qw;
-              const uint4 val = *reinterpret_cast<const uint4*>(sStage + r * pitch + chk * 16);
+              const uint4 val = *reinterpret_cast<const uint4*>(sbuf + r * pitch + chk * 16);
               *reinterpret_cast<uint4*>(gbase + pix * p.out_cs * es) = val;
             }
           }
         }
+        ++pass_ctr;
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
     }
+    if (p.tma_store && gt == 0) tma_store_wait_read<0>();   // smem must outlive the bulk stores' reads (global completion is tracked by the grid)
   }
 
-  if (p.tma_store && threadIdx.x == 128) tma_store_wait_read<0>();   // smem must outlive the bulk stores' reads (global completion is tracked by the grid)
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
+  if (p.trace && threadIdx.x == 0) atomicMax(p.trace + 2, globaltimer_ns());
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -746,8 +771,18 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
   p.res = d.res; p.res_cs = d.res_cs; p.res_co = d.res_co;
   p.out_ns = d.out_ns > 0 ? d.out_ns : Hout * Wout;
 
-  // ---- smem budget -> pipeline depth
-  const int CH = d.out_f32 ? (BN < 64 ? BN : 64) : (BN < 128 ? BN : 128);
+  // ---- epilogue groups / staging / smem budget -> pipeline depth
+  // Preferred: 4 groups of 4 warps with 16-KB staging each (BN <= 128: four 128-column TMEM slots), 2 groups of 8 warps
+  // with 32-KB staging each for BN = 256.  When that staging would squeeze the load pipeline (fewer than 3 halo buffers /
+  // 4 stages) the next level halves it: 2 groups of 4 warps (BN <= 128) / 64-column passes (BN = 256).
+  static const int nacc_env = getenv("CC_NACC") ? atoi(getenv("CC_NACC")) : 4;
+  int level = (BN <= 128 && nacc_env == 2) ? 1 : 0;
+budget_again:
+  if (BN > 128) { p.n_acc = 2; p.lgw = 3; }
+  else { p.n_acc = level == 0 ? 4 : 2; p.lgw = 2; }
+  int CH = (p.lgw == 2 || level >= 1) ? (d.out_f32 ? 32 : 64) : (d.out_f32 ? 64 : 128);
+  if (CH > BN) CH = BN;
+  p.CH = CH;
   static const int tmas_env = getenv("CC_TMASTORE") ? atoi(getenv("CC_TMASTORE")) : 1;
   static const int tmas64_env = getenv("CC_TMASTORE64") ? atoi(getenv("CC_TMASTORE64")) : 1;
   p.stg_lrow = 7;
@@ -756,14 +791,7 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
     p.tma_store = 1;
     p.stg_lrow = 6;
   }
-  p.stg_bufs = 1;
   if (p.tma_store) {
-    // double-buffer the staging when the pipeline still gets >= 4 stages (per-tap mode) / 3 B stages (halo mode)
-    const int one = kTileM * CH * es;
-    const int stage_b = p.halo ? BN * p.BK * 2 : kTileM * p.BK * 2 + BN * p.BK * 2;
-    const int other = 1024 + d.Cout * 4 + 320;
-    if (!p.halo && (kMaxSmem - other - 2 * one) / stage_b >= 4) p.stg_bufs = 2;
-    if (p.halo && kMaxSmem - other - 2 * one - 3 * stage_b >= 3 * p.halo_bytes) p.stg_bufs = 2;
     void* base = reinterpret_cast<uint8_t*>(d.out) + size_t(d.out_co) * es;
     cuuint64_t dims[5], strides[4];
     cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
@@ -788,12 +816,14 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
   p.res_tma = (restma_env && p.tma_store && d.res != nullptr && d.res == d.out && d.res_cs == d.out_cs && d.res_co == d.out_co) ? 1 : 0;
   if (p.res_tma && d.out_f32 && restma_env >= 1 && restma_env != 3) p.res_tma = 2;   // fp32: reduce-add store (CC_RES_TMA=3 forces the prefetch variant)
   const int pitch = p.tma_store ? CH * es : CH * es + 16;
-  const int staging = ((kTileM * pitch + 15) & ~15) * (p.tma_store ? p.stg_bufs : 1);
+  const int staging = ((kTileM * pitch + 15) & ~15) * p.n_acc;
   const int stage_bytes = kTileM * p.BK * 2 + BN * p.BK * 2;
-  const int fixed = 1024 /*align slack*/ + staging + d.Cout * 4 /*bias*/ + 320 /*barriers*/;
+  const int fixed = 1024 /*alignment slack of the smem base*/ + staging + d.Cout * 4 /*bias*/ + 304 /*barriers + TMEM slot*/;
+  // the staging area starts at the next 1024-B boundary after the operand rings (a no-op unless a weight tile is an odd
+  // multiple of 512 B)
+  auto stage_pad = [](int operand_bytes) { return (1024 - operand_bytes % 1024) % 1024; };
   int S;
   static const int bres_env = getenv("CC_BRES") ? atoi(getenv("CC_BRES")) : 1;
-  static const int epidyn_env = getenv("CC_EPI_DYN") ? atoi(getenv("CC_EPI_DYN")) : 1;
   static const int dbg_env = getenv("CC_DBG") ? atoi(getenv("CC_DBG")) : 0;
   p.dbg = dbg_env;
   {
@@ -807,9 +837,6 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
     fast_div(p.tiles_w, p.fd_tw);
     fast_div(p.tiles_h, p.fd_th);
     fast_div(p.tiles_w * p.tiles_h, p.fd_twh);
-    const int CHh = d.out_f32 ? (BN < 64 ? BN : 64) : (BN < 128 ? BN : 128);
-    const int groups = CHh / 16 < kColGroups ? CHh / 16 : kColGroups;
-    p.epi_threads = epidyn_env ? 128 * groups : kEpiThreads;
   }
   static const int hst_env = getenv("CC_HALO_STAGES") ? atoi(getenv("CC_HALO_STAGES")) : 0;
   const int bres_bytes = BN * p.BK * 2 * p.num_taps * p.chunks_per_tap;
@@ -831,23 +858,33 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
     int hs = (avail - wbytes) / p.halo_bytes;
     if (hs > 4) hs = 4;
     if (hst_env >= 2 && hst_env <= 4 && hst_env < hs) hs = hst_env;
+    if (hs < 3 && level == 0) {   // the staging squeezes the halo ring: halve it (an MMA-bound layer does not need more)
+      level = 1;
+      goto budget_again;
+    }
     if (hs < 2) {   // does not fit: caller falls back
       set_error("conv_gemm: halo tile does not fit (BN=%d halo=%d B)", BN, p.halo_bytes);
       return CC_ERR_INVALID;
     }
     p.halo_stages = hs;
-    L->smem_bytes = fixed + wbytes + hs * p.halo_bytes;
+    L->smem_bytes = fixed + wbytes + hs * p.halo_bytes + stage_pad(wbytes + hs * p.halo_bytes);
   } else if (p.b_res && (kMaxSmem - fixed - bres_bytes) / (kTileM * p.BK * 2) >= 4) {
     const int a_bytes = kTileM * p.BK * 2;
     S = (kMaxSmem - fixed - bres_bytes) / a_bytes;
     if (S > 8) S = 8;
-    L->smem_bytes = fixed + bres_bytes + S * a_bytes;
+    if (fixed + bres_bytes + S * a_bytes + stage_pad(bres_bytes + S * a_bytes) > kMaxSmem) --S;
+    L->smem_bytes = fixed + bres_bytes + S * a_bytes + stage_pad(bres_bytes + S * a_bytes);
   } else {
     p.b_res = 0;
     S = (kMaxSmem - fixed) / stage_bytes;
     if (S > 8) S = 8;
+    if (S < 4 && level == 0) {
+      level = 1;
+      goto budget_again;
+    }
+    if (fixed + S * stage_bytes + stage_pad(S * stage_bytes) > kMaxSmem) --S;
     CC_REQUIRE(S >= 2, "conv_gemm: tile does not fit shared memory (BN=%d BK=%d)", BN, p.BK);
-    L->smem_bytes = fixed + S * stage_bytes;
+    L->smem_bytes = fixed + S * stage_bytes + stage_pad(S * stage_bytes);
   }
   p.stages = S;
   L->grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;

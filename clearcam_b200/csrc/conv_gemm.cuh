@@ -44,7 +44,7 @@ struct GemmParams {
   // the nine taps are shifted shared-memory descriptor views of it
   int32_t halo, halo_bytes, halo_bo;  // enabled / bytes per halo stage / descriptor base_offset mode
   int32_t halo_stages;                // 2..4 halo buffers in flight
-  int32_t tma_store, stg_bufs;        // epilogue stores through TMA from 128B-swizzled staging (1 or 2 buffers)
+  int32_t tma_store;                  // epilogue stores through TMA from swizzled staging (one buffer per epilogue group)
   int32_t b_res;                      // weights of the (single) N block stay resident in smem for the whole kernel
   int32_t res_tma;                    // in-place residual is prefetched into the staging buffer by TMA (through tmC)
   // tile index -> (n block, w, h, n) without integer division: q = (umulhi(mul, x) + x) >> shift (per-tile index
@@ -52,7 +52,10 @@ struct GemmParams {
   uint32_t fd_nb[2], fd_tw[2], fd_th[2], fd_twh[2];
   int32_t stg_lrow;                   // log2 of the staging / TMA-store row: 7 (SWIZZLE_128B) or 6 (SWIZZLE_64B, narrow tiles)
   int32_t dbg;                        // CC_DBG bisection switches (never set in production): 1 no epilogue work, 4 no A loads
-  int32_t epi_threads;                // epilogue threads that have columns to convert: 128 * min(4, BN/16)
+  int32_t n_acc;                      // TMEM accumulator slots == independent epilogue groups: 4 (BN <= 128) or 2
+  int32_t lgw;                        // log2(warps per epilogue group): 2 or 3
+  int32_t CH;                         // output columns per staging pass of one epilogue group
+  unsigned long long* trace;          // optional device timeline slot [3]: first CTA entry, dependency released, last CTA exit (globaltimer ns)
 };
 
 struct ConvDesc {

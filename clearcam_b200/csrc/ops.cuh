@@ -22,11 +22,18 @@ struct DirectConvParams {
 };
 int conv_direct_launch(const DirectConvParams& p, cudaStream_t stream);
 
-// A bf16 NHWC tensor slice.
+// An NHWC tensor slice: bf16 elements, or float when f32 != 0 (fp32-accurate mode; cs / co / C count elements either way
+// and p is then really a float*).
 struct TSlice {
   __nv_bfloat16* p; int cs, co, C;   // buffer base, channels per pixel, first channel, channel count
   int N, H, W;
+  int f32;
 };
+
+// fp32-accurate mode: fp32 activation slice -> six bf16 planes per pixel [lo | mid | hi | mid | hi | hi] (x = hi + mid + lo
+// exactly, each a bf16), the A operand of a tensor-core conv whose weights are laid out [hi | mid | lo | hi | mid | hi]:
+// the six products with combined weight >= 2^-16 of an fp32 x fp32 product, smallest first.  out: dense [N*H*W][6*C] bf16.
+int split_planes_launch(const TSlice& in, __nv_bfloat16* out, cudaStream_t s);
 
 // avg_pool2d(k=2,s=1,p=0) written into a same-size map whose last row/col are zero (so the stride-2 conv that
 // follows can use the even "pixel pair" TMA view).  detection/yolov9.py:47 (ADown), :62 (AConv).
@@ -99,5 +106,7 @@ size_t attention_tc_workspace_bytes(int B, int L, int H);
 int attention_tc_launch(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, __nv_bfloat16* vt_ws, int B, int L, int H, int causal,
                         cudaStream_t st);
 int search_scores_launch(const float* index, const float* q, float* scores, int N, int D, int Q, cudaStream_t st);
+int search_topk_launch(const float* index, const float* q, const int* group, const uint8_t* mask, unsigned long long* best, int N, int D,
+                       int G, int k, int* out_rows, float* out_scores, cudaStream_t st);
 
 }  // namespace cc

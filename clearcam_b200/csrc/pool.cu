@@ -9,33 +9,64 @@ namespace cc {
 
 struct bf8 { float v[8]; };
 
-__device__ __forceinline__ bf8 ld8(const __nv_bfloat16* p) {
-  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
-  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-  bf8 r;
+// Element type of a slice: bf16 (default path) or float (fp32-accurate mode, TSlice::f32).  All kernels below compute in
+// fp32 either way; only the loads / stores of 8 consecutive channels differ.
+template <typename E> struct Vec8;
+template <> struct Vec8<__nv_bfloat16> {
+  typedef uint4 raw_t;                                       // 8 packed elements as loaded (kept packed while in flight)
+  static __device__ __forceinline__ raw_t ld_raw(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+  static __device__ __forceinline__ bf8 ld(const __nv_bfloat16* p) { return unpack(ld_raw(p)); }
+  static __device__ __forceinline__ bf8 unpack(const raw_t& u) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    bf8 r;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
-    r.v[2 * i] = __bfloat162float(h.x);
-    r.v[2 * i + 1] = __bfloat162float(h.y);
+    for (int i = 0; i < 4; ++i) {
+      r.v[2 * i] = __uint_as_float(w[i] << 16);            // bf16 -> fp32 is a shift
+      r.v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+    return r;
   }
-  return r;
-}
-__device__ __forceinline__ void st8(__nv_bfloat16* p, const bf8& r) {
-  uint32_t w[4];
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, const bf8& r) {
+    uint32_t w[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(r.v[2 * i], r.v[2 * i + 1]);
-    w[i] = *reinterpret_cast<uint32_t*>(&h);
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(r.v[2 * i], r.v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
   }
-  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  static __device__ __forceinline__ float round_store(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+};
+template <> struct Vec8<float> {
+  typedef bf8 raw_t;
+  static __device__ __forceinline__ raw_t ld_raw(const float* p) { return ld(p); }
+  static __device__ __forceinline__ bf8 unpack(const raw_t& u) { return u; }
+  static __device__ __forceinline__ bf8 ld(const float* p) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    bf8 r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+  }
+  static __device__ __forceinline__ void st(float* p, const bf8& r) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
+  }
+  static __device__ __forceinline__ float round_store(float x) { return x; }
+};
+template <typename E>
+__device__ __forceinline__ const E* at(const TSlice& t, int n, int h, int w, int c) {
+  return reinterpret_cast<const E*>(t.p) + ((static_cast<long long>(n) * t.H + h) * t.W + w) * t.cs + t.co + c;
 }
-__device__ __forceinline__ const __nv_bfloat16* at(const TSlice& t, int n, int h, int w, int c) {
-  return t.p + ((static_cast<long long>(n) * t.H + h) * t.W + w) * t.cs + t.co + c;
+template <typename E>
+__device__ __forceinline__ E* at_w(const TSlice& t, int n, int h, int w, int c) {
+  return reinterpret_cast<E*>(t.p) + ((static_cast<long long>(n) * t.H + h) * t.W + w) * t.cs + t.co + c;
 }
-__device__ __forceinline__ __nv_bfloat16* at_w(const TSlice& t, int n, int h, int w, int c) {
-  return t.p + ((static_cast<long long>(n) * t.H + h) * t.W + w) * t.cs + t.co + c;
-}
+// launch KERNEL<bf16> or KERNEL<float> by the slice's element type
+#define CC_LAUNCH_E(KERNEL, F32, GRID, BLOCK, STREAM, ...)                                   \
+  do {                                                                                        \
+    if (F32) KERNEL<float><<<GRID, BLOCK, 0, STREAM>>>(__VA_ARGS__);                          \
+    else KERNEL<__nv_bfloat16><<<GRID, BLOCK, 0, STREAM>>>(__VA_ARGS__);                      \
+  } while (0)
 
 static int grid_for(long long total, int threads) {
   long long b = (total + threads - 1) / threads;
@@ -71,28 +102,30 @@ static int row_threads(const TSlice& out) {
 }
 
 // ---------------------------------------------------------------- avg 2x2 s1 -> same-size zero-edged map
+template <typename E>
 __global__ void avgpool2_pad_kernel(TSlice in, TSlice out) {
   const RowIdx q = row_index(out.W, in.C / 8);
   if (!q.ok) return;
   bf8 r;
   if (q.h < in.H - 1 && q.w < in.W - 1) {
-    const __nv_bfloat16* p0 = at(in, q.n, q.h, q.w, q.c);
-    const __nv_bfloat16* p1 = p0 + static_cast<long long>(in.W) * in.cs;
-    const bf8 a = ld8(p0), b = ld8(p0 + in.cs), d = ld8(p1), e = ld8(p1 + in.cs);
+    const E* p0 = at<E>(in, q.n, q.h, q.w, q.c);
+    const E* p1 = p0 + static_cast<long long>(in.W) * in.cs;
+    const bf8 a = Vec8<E>::ld(p0), b = Vec8<E>::ld(p0 + in.cs), d = Vec8<E>::ld(p1), e = Vec8<E>::ld(p1 + in.cs);
 #pragma unroll
     for (int i = 0; i < 8; ++i) r.v[i] = ((a.v[i] + b.v[i]) + (d.v[i] + e.v[i])) * 0.25f;
   } else {
 #pragma unroll
     for (int i = 0; i < 8; ++i) r.v[i] = 0.f;
   }
-  st8(at_w(out, q.n, q.h, q.w, q.c), r);
+  Vec8<E>::st(at_w<E>(out, q.n, q.h, q.w, q.c), r);
 }
 int avgpool2_pad_launch(const TSlice& in, const TSlice& out, cudaStream_t s) {
   CC_REQUIRE(in.C % 8 == 0 && in.co % 8 == 0 && in.cs % 8 == 0 && out.co % 8 == 0 && out.cs % 8 == 0 && in.C == out.C &&
                  in.H == out.H && in.W == out.W, "avgpool2_pad: bad slices");
   CC_REQUIRE(out.H <= 65535 && out.N <= 65535, "avgpool2_pad: tensor too large for the row grid");
   const int t = row_threads(out);
-  avgpool2_pad_kernel<<<row_grid(out, t), t, 0, s>>>(in, out);
+  CC_REQUIRE(in.f32 == out.f32, "avgpool2_pad: mixed element types");
+  CC_LAUNCH_E(avgpool2_pad_kernel, in.f32, row_grid(out, t), t, s, in, out);
   CC_CHECK_CUDA(cudaGetLastError());
   return CC_OK;
 }
@@ -102,14 +135,7 @@ int avgpool2_pad_launch(const TSlice& in, const TSlice& out, cudaStream_t s) {
 // avg = ((a+b)+(d+e))*0.25 rounded to bf16 first (the reference max-pools the stored avg map).  Separable: the row-pair
 // sums (a+b) are shared by vertically adjacent averages, so the 4x4 input window is read once (16 vector loads instead of
 // 36) and the additions keep the reference's order.
-__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
-  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    f[2 * i] = __uint_as_float(w[i] << 16);           // bf16 -> fp32 is a shift
-    f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
-  }
-}
+template <typename E>
 __global__ void __launch_bounds__(256, 2) avgmax_pool_kernel(TSlice in, TSlice out) {
   const RowIdx q = row_index(out.W, in.C / 8);
   if (!q.ok) return;
@@ -117,15 +143,15 @@ __global__ void __launch_bounds__(256, 2) avgmax_pool_kernel(TSlice in, TSlice o
   const int y0 = 2 * q.h - 1, x0 = 2 * q.w - 1;
   // all 16 vector loads of the 4x4 window go out first (clamped coordinates: always in bounds, never used when the
   // position is outside the map) — the kernel is latency-bound, so bytes in flight per SM are what buys bandwidth
-  uint4 raw[4][4];
-  const __nv_bfloat16* base = at(in, q.n, 0, 0, q.c);
+  typename Vec8<E>::raw_t raw[4][4];
+  const E* base = at<E>(in, q.n, 0, 0, q.c);
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     const int y = min(max(y0 + r, 0), in.H - 1);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       const int x = min(max(x0 + c, 0), in.W - 1);
-      raw[r][c] = __ldg(reinterpret_cast<const uint4*>(base + (static_cast<long long>(y) * in.W + x) * in.cs));
+      raw[r][c] = Vec8<E>::ld_raw(base + (static_cast<long long>(y) * in.W + x) * in.cs);
     }
   }
   bool cv[3];
@@ -137,16 +163,16 @@ __global__ void __launch_bounds__(256, 2) avgmax_pool_kernel(TSlice in, TSlice o
   float hp[3][8];                    // row-pair sums (a+b) of the previous input row
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
-    float v0[8], v1[8], v2[8], v3[8], h[3][8];
-    unpack8(raw[r][0], v0);
-    unpack8(raw[r][1], v1);
-    unpack8(raw[r][2], v2);
-    unpack8(raw[r][3], v3);
+    float h[3][8];
+    {
+      const bf8 v0 = Vec8<E>::unpack(raw[r][0]), v1 = Vec8<E>::unpack(raw[r][1]), v2 = Vec8<E>::unpack(raw[r][2]),
+                v3 = Vec8<E>::unpack(raw[r][3]);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      h[0][i] = v0[i] + v1[i];
-      h[1][i] = v1[i] + v2[i];
-      h[2][i] = v2[i] + v3[i];
+      for (int i = 0; i < 8; ++i) {
+        h[0][i] = v0.v[i] + v1.v[i];
+        h[1][i] = v1.v[i] + v2.v[i];
+        h[2][i] = v2.v[i] + v3.v[i];
+      }
     }
     if (r >= 1) {
       const int ya = y0 + r - 1;     // avg row = input rows (ya, ya+1)
@@ -156,7 +182,7 @@ __global__ void __launch_bounds__(256, 2) avgmax_pool_kernel(TSlice in, TSlice o
           if (cv[c]) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float av = __bfloat162float(__float2bfloat16_rn((hp[c][i] + h[c][i]) * 0.25f));
+              const float av = Vec8<E>::round_store((hp[c][i] + h[c][i]) * 0.25f);   // the reference max-pools the STORED avg map
               m[i] = fmaxf(m[i], av);
             }
           }
@@ -171,7 +197,7 @@ __global__ void __launch_bounds__(256, 2) avgmax_pool_kernel(TSlice in, TSlice o
   bf8 o;
 #pragma unroll
   for (int i = 0; i < 8; ++i) o.v[i] = m[i];
-  st8(at_w(out, q.n, q.h, q.w, q.c), o);
+  Vec8<E>::st(at_w<E>(out, q.n, q.h, q.w, q.c), o);
 }
 int avgmax_pool_launch(const TSlice& in, const TSlice& out, cudaStream_t s) {
   CC_REQUIRE(in.C % 8 == 0 && in.co % 8 == 0 && in.cs % 8 == 0 && out.co % 8 == 0 && out.cs % 8 == 0 && in.C == out.C,
@@ -179,12 +205,14 @@ int avgmax_pool_launch(const TSlice& in, const TSlice& out, cudaStream_t s) {
   CC_REQUIRE(out.H == (in.H - 1 + 2 - 3) / 2 + 1 && out.W == (in.W - 1 + 2 - 3) / 2 + 1, "avgmax_pool: bad output extent");
   CC_REQUIRE(out.H <= 65535 && out.N <= 65535, "avgmax_pool: tensor too large for the row grid");
   const int t = row_threads(out);
-  avgmax_pool_kernel<<<row_grid(out, t), t, 0, s>>>(in, out);
+  CC_REQUIRE(in.f32 == out.f32, "avgmax_pool: mixed element types");
+  CC_LAUNCH_E(avgmax_pool_kernel, in.f32, row_grid(out, t), t, s, in, out);
   CC_CHECK_CUDA(cudaGetLastError());
   return CC_OK;
 }
 
 // ---------------------------------------------------------------- max 5x5 s1 p2
+template <typename E>
 __global__ void maxpool5_kernel(TSlice in, TSlice out) {
   const RowIdx q = row_index(out.W, in.C / 8);
   if (!q.ok) return;
@@ -197,41 +225,47 @@ __global__ void maxpool5_kernel(TSlice in, TSlice out) {
     for (int dx = -2; dx <= 2; ++dx) {
       const int x = q.w + dx;
       if (x < 0 || x >= in.W) continue;
-      const bf8 a = ld8(at(in, q.n, y, x, q.c));
+      const bf8 a = Vec8<E>::ld(at<E>(in, q.n, y, x, q.c));
 #pragma unroll
       for (int i = 0; i < 8; ++i) m.v[i] = fmaxf(m.v[i], a.v[i]);
     }
   }
-  st8(at_w(out, q.n, q.h, q.w, q.c), m);
+  Vec8<E>::st(at_w<E>(out, q.n, q.h, q.w, q.c), m);
 }
 int maxpool5_launch(const TSlice& in, const TSlice& out, cudaStream_t s) {
   CC_REQUIRE(in.C % 8 == 0 && in.co % 8 == 0 && in.cs % 8 == 0 && out.co % 8 == 0 && out.cs % 8 == 0 && in.C == out.C &&
                  in.H == out.H && in.W == out.W, "maxpool5: bad slices");
   CC_REQUIRE(out.H <= 65535 && out.N <= 65535, "maxpool5: tensor too large for the row grid");
   const int t = row_threads(out);
-  maxpool5_kernel<<<row_grid(out, t), t, 0, s>>>(in, out);
+  CC_REQUIRE(in.f32 == out.f32, "maxpool5: mixed element types");
+  CC_LAUNCH_E(maxpool5_kernel, in.f32, row_grid(out, t), t, s, in, out);
   CC_CHECK_CUDA(cudaGetLastError());
   return CC_OK;
 }
 
 // ---------------------------------------------------------------- nearest x2
+template <typename E>
 __global__ void upsample2_kernel(TSlice in, TSlice out) {
   const RowIdx q = row_index(out.W, in.C / 8);
   if (!q.ok) return;
-  const uint4 v = __ldg(reinterpret_cast<const uint4*>(at(in, q.n, q.h >> 1, q.w >> 1, q.c)));
-  *reinterpret_cast<uint4*>(at_w(out, q.n, q.h, q.w, q.c)) = v;
+  const uint4* src = reinterpret_cast<const uint4*>(at<E>(in, q.n, q.h >> 1, q.w >> 1, q.c));
+  uint4* dst = reinterpret_cast<uint4*>(at_w<E>(out, q.n, q.h, q.w, q.c));
+#pragma unroll
+  for (int i = 0; i < static_cast<int>(sizeof(E)) / 2; ++i) dst[i] = __ldg(src + i);   // 8 channels = 16 B (bf16) or 32 B (float)
 }
 int upsample2_launch(const TSlice& in, const TSlice& out, cudaStream_t s) {
   CC_REQUIRE(in.C % 8 == 0 && in.co % 8 == 0 && in.cs % 8 == 0 && out.co % 8 == 0 && out.cs % 8 == 0 && in.C == out.C &&
                  out.H == 2 * in.H && out.W == 2 * in.W, "upsample2: bad slices");
   CC_REQUIRE(out.H <= 65535 && out.N <= 65535, "upsample2: tensor too large for the row grid");
   const int t = row_threads(out);
-  upsample2_kernel<<<row_grid(out, t), t, 0, s>>>(in, out);
+  CC_REQUIRE(in.f32 == out.f32, "upsample2: mixed element types");
+  CC_LAUNCH_E(upsample2_kernel, in.f32, row_grid(out, t), t, s, in, out);
   CC_CHECK_CUDA(cudaGetLastError());
   return CC_OK;
 }
 
 // ---------------------------------------------------------------- CBFuse
+template <typename E>
 __global__ void cbfuse_kernel(CBFuseParams p) {
   const RowIdx q = row_index(p.out.W, p.out.C / 8);
   if (!q.ok) return;
@@ -242,20 +276,64 @@ __global__ void cbfuse_kernel(CBFuseParams p) {
     // nearest: src = floor(dst * in / out)
     const int sh = (q.h * p.src[k].H) / p.out.H;
     const int sw = (q.w * p.src[k].W) / p.out.W;
-    const bf8 a = ld8(at(p.src[k], q.n, sh, sw, q.c));
+    const bf8 a = Vec8<E>::ld(at<E>(p.src[k], q.n, sh, sw, q.c));
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc.v[i] = (k == 0) ? a.v[i] : acc.v[i] + a.v[i];
   }
-  const bf8 l = ld8(at(p.last, q.n, q.h, q.w, q.c));
+  const bf8 l = Vec8<E>::ld(at<E>(p.last, q.n, q.h, q.w, q.c));
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc.v[i] += l.v[i];
-  st8(at_w(p.out, q.n, q.h, q.w, q.c), acc);
+  Vec8<E>::st(at_w<E>(p.out, q.n, q.h, q.w, q.c), acc);
 }
 int cbfuse_launch(const CBFuseParams& p, cudaStream_t s) {
   CC_REQUIRE(p.nsrc >= 1 && p.nsrc <= 5 && p.out.C % 8 == 0, "cbfuse: bad params");
   CC_REQUIRE(p.out.H <= 65535 && p.out.N <= 65535, "cbfuse: tensor too large for the row grid");
   const int t = row_threads(p.out);
-  cbfuse_kernel<<<row_grid(p.out, t), t, 0, s>>>(p);
+  CC_LAUNCH_E(cbfuse_kernel, p.out.f32, row_grid(p.out, t), t, s, p);
+  CC_CHECK_CUDA(cudaGetLastError());
+  return CC_OK;
+}
+
+// ---------------------------------------------------------------- fp32 -> six bf16 planes (fp32-accurate mode)
+// one thread = one pixel x 4 channels: float4 in, six 8-byte stores out (plane p of pixel i at out[i*6C + p*C + c])
+__global__ void split_planes_kernel(const float* __restrict__ in, long long npix, int cs, int co, int C, __nv_bfloat16* __restrict__ out) {
+  const int c4n = C >> 2;
+  const long long total = npix * c4n;
+  CC_GRID_STRIDE(idx, total) {
+    const long long pix = idx / c4n;
+    const int c = static_cast<int>(idx - pix * c4n) << 2;
+    const float4 x = __ldg(reinterpret_cast<const float4*>(in + pix * cs + co + c));
+    const float xs[4] = {x.x, x.y, x.z, x.w};
+    uint32_t hi[2], mid[2], lo[2];
+    __nv_bfloat16 h[4], m[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      h[j] = __float2bfloat16_rn(xs[j]);
+      const float r1 = xs[j] - __bfloat162float(h[j]);          // exact (Sterbenz-like: the bf16 is within half an ulp)
+      m[j] = __float2bfloat16_rn(r1);
+      const float r2 = r1 - __bfloat162float(m[j]);             // exact
+      l[j] = __float2bfloat16_rn(r2);                           // 8 + 8 + 8 mantissa bits: x == hi + mid + lo
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      __nv_bfloat162 t;
+      t.x = h[2 * j]; t.y = h[2 * j + 1]; hi[j] = *reinterpret_cast<uint32_t*>(&t);
+      t.x = m[2 * j]; t.y = m[2 * j + 1]; mid[j] = *reinterpret_cast<uint32_t*>(&t);
+      t.x = l[2 * j]; t.y = l[2 * j + 1]; lo[j] = *reinterpret_cast<uint32_t*>(&t);
+    }
+    __nv_bfloat16* o = out + pix * (6LL * C) + c;
+    *reinterpret_cast<uint2*>(o) = make_uint2(lo[0], lo[1]);
+    *reinterpret_cast<uint2*>(o + C) = make_uint2(mid[0], mid[1]);
+    *reinterpret_cast<uint2*>(o + 2 * C) = make_uint2(hi[0], hi[1]);
+    *reinterpret_cast<uint2*>(o + 3 * C) = make_uint2(mid[0], mid[1]);
+    *reinterpret_cast<uint2*>(o + 4 * C) = make_uint2(hi[0], hi[1]);
+    *reinterpret_cast<uint2*>(o + 5 * C) = make_uint2(hi[0], hi[1]);
+  }
+}
+int split_planes_launch(const TSlice& in, __nv_bfloat16* out, cudaStream_t s) {
+  CC_REQUIRE(in.f32 && in.C % 4 == 0 && in.co % 4 == 0 && in.cs % 4 == 0, "split_planes: needs an fp32 slice with 16-byte aligned channels");
+  const long long npix = static_cast<long long>(in.N) * in.H * in.W;
+  split_planes_kernel<<<grid_for(npix * (in.C / 4), 256), 256, 0, s>>>(reinterpret_cast<const float*>(in.p), npix, in.cs, in.co, in.C, out);
   CC_CHECK_CUDA(cudaGetLastError());
   return CC_OK;
 }
@@ -330,7 +408,8 @@ int letterbox_launch(const LetterboxParams& p, cudaStream_t s) {
 // ---------------------------------------------------------------- stem conv (Cin = 3)
 // block = 128 threads = 128 consecutive output pixels of one row-major run; weights (27 x Cout fp32) in smem.
 // Each thread gathers its 27 inputs once (RGB order, /255) and produces all Cout channels, 16 at a time.
-template <bool F32>
+// F32: float frames (else uint8);  E: output element type (float = fp32-accurate mode: exact division in the SiLU)
+template <bool F32, typename E>
 __global__ void __launch_bounds__(128) stem_kernel(StemParams p) {
   extern __shared__ float sw[];  // [27][Cout] then bias[Cout]
   const int Cout = p.Cout;
@@ -368,7 +447,7 @@ __global__ void __launch_bounds__(128) stem_kernel(StemParams p) {
         }
       }
     }
-    __nv_bfloat16* dst = p.out.p + ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * p.out.cs + p.out.co;
+    E* dst = reinterpret_cast<E*>(p.out.p) + ((static_cast<long long>(n) * Ho + oy) * Wo + ox) * p.out.cs + p.out.co;
     for (int c0 = 0; c0 < Cout; c0 += 8) {
       float acc[8];
 #pragma unroll
@@ -384,8 +463,9 @@ __global__ void __launch_bounds__(128) stem_kernel(StemParams p) {
       }
       bf8 o;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o.v[j] = __fdividef(acc[j], 1.0f + __expf(-acc[j]));
-      st8(dst + c0, o);
+      for (int j = 0; j < 8; ++j)
+        o.v[j] = sizeof(E) == 4 ? acc[j] / (1.0f + expf(-acc[j])) : __fdividef(acc[j], 1.0f + __expf(-acc[j]));
+      Vec8<E>::st(dst + c0, o);
     }
   }
 }
@@ -440,8 +520,13 @@ int stem_launch(const StemParams& p, cudaStream_t s) {
   const int smem = (27 + 1) * p.Cout * sizeof(float);
   long long blocks = (total + 127) / 128;
   if (blocks > 148LL * 16) blocks = 148LL * 16;
-  if (p.is_f32) stem_kernel<true><<<static_cast<int>(blocks), 128, smem, s>>>(p);
-  else stem_kernel<false><<<static_cast<int>(blocks), 128, smem, s>>>(p);
+  if (p.out.f32) {
+    if (p.is_f32) stem_kernel<true, float><<<static_cast<int>(blocks), 128, smem, s>>>(p);
+    else stem_kernel<false, float><<<static_cast<int>(blocks), 128, smem, s>>>(p);
+  } else {
+    if (p.is_f32) stem_kernel<true, __nv_bfloat16><<<static_cast<int>(blocks), 128, smem, s>>>(p);
+    else stem_kernel<false, __nv_bfloat16><<<static_cast<int>(blocks), 128, smem, s>>>(p);
+  }
   CC_CHECK_CUDA(cudaGetLastError());
   return CC_OK;
 }

@@ -449,4 +449,92 @@ int search_scores_launch(const float* index, const float* q, float* scores, int 
   return CC_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------ search, top-k on the device
+// ObjectFinder.search (models/objects.py:356-390) keeps, per object id, the best-scoring image and returns the k best of
+// those.  Here: (1) one warp per index row computes the dot product and folds it into its group's best with one 64-bit
+// atomicMax on (orderable score << 32 | ~row) — a row of an earlier index wins an exact tie; (2) one CTA extracts the k best
+// groups.  Only k (row, score) pairs cross PCIe instead of N scores.
+__device__ __forceinline__ uint32_t f32_orderable(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float f32_from_orderable(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+__global__ void search_group_best_kernel(const float* __restrict__ index, const float* __restrict__ q, const int* __restrict__ group,
+                                         const uint8_t* __restrict__ mask, unsigned long long* __restrict__ best, int N, int D) {
+  extern __shared__ float sq[];  // [D]
+  for (int i = threadIdx.x; i < D; i += blockDim.x) sq[i] = q[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int n = blockIdx.x * wpb + (threadIdx.x >> 5); n < N; n += gridDim.x * wpb) {
+    if (mask && !mask[n]) continue;
+    const float* row = index + static_cast<long long>(n) * D;
+    float acc = 0.f;
+    for (int c = lane; c < D; c += 32) acc = fmaf(__ldg(row + c), sq[c], acc);     // same summation order as search_scores_kernel
+    const float s = warp_sum(acc);
+    if (lane == 0)
+      atomicMax(best + group[n], (static_cast<unsigned long long>(f32_orderable(s)) << 32) | (0xFFFFFFFFu - static_cast<uint32_t>(n)));
+  }
+}
+__global__ void __launch_bounds__(1024) search_topk_kernel(unsigned long long* __restrict__ best, int G, int k, int* __restrict__ out_rows,
+                                                           float* __restrict__ out_scores) {
+  __shared__ unsigned long long s_key[32];
+  __shared__ int s_idx[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int r = 0; r < k; ++r) {
+    unsigned long long bk = 0;
+    int bi = -1;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+      const unsigned long long v = best[g];
+      if (v > bk) { bk = v; bi = g; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long ok = __shfl_xor_sync(0xFFFFFFFFu, bk, o);
+      const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
+      if (ok > bk) { bk = ok; bi = oi; }
+    }
+    if (lane == 0) { s_key[warp] = bk; s_idx[warp] = bi; }
+    __syncthreads();
+    if (warp == 0) {
+      bk = lane < (blockDim.x >> 5) ? s_key[lane] : 0ull;
+      bi = lane < (blockDim.x >> 5) ? s_idx[lane] : -1;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long ok = __shfl_xor_sync(0xFFFFFFFFu, bk, o);
+        const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
+        if (ok > bk) { bk = ok; bi = oi; }
+      }
+      if (lane == 0) {
+        if (bi >= 0) {
+          out_rows[r] = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(bk & 0xFFFFFFFFull));
+          out_scores[r] = f32_from_orderable(static_cast<uint32_t>(bk >> 32));
+          best[bi] = 0ull;                       // taken
+        } else {
+          out_rows[r] = -1;                      // fewer than k groups matched
+          out_scores[r] = 0.f;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+int search_topk_launch(const float* index, const float* q, const int* group, const uint8_t* mask, unsigned long long* best, int N, int D,
+                       int G, int k, int* out_rows, float* out_scores, cudaStream_t st) {
+  CC_REQUIRE(D * 4 <= 48 * 1024, "search: %d dims exceed the 48 KB query buffer", D);
+  CC_CHECK_CUDA(cudaMemsetAsync(best, 0, static_cast<size_t>(G > 0 ? G : 1) * sizeof(unsigned long long), st));
+  if (N > 0) {
+    int blocks = (N + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    search_group_best_kernel<<<blocks, 256, D * 4, st>>>(index, q, group, mask, best, N, D);
+    CC_CHECK_CUDA(cudaGetLastError());
+  }
+  search_topk_kernel<<<1, 1024, 0, st>>>(best, G, k, out_rows, out_scores);
+  CC_CHECK_CUDA(cudaGetLastError());
+  return CC_OK;
+}
+
 }  // namespace cc

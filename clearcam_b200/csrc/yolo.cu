@@ -145,16 +145,17 @@ struct ConvW {           // device-resident, kernel layout
   __nv_bfloat16* w = nullptr;   // [Cout][k][k][Cin_eff]  (Cin_eff = Cin when dense, Cin/groups when grouped)
   float* wf32 = nullptr;        // stem only: fp32 [Cout][3][3][3]
   __nv_bfloat16* wtc = nullptr; // stem only: bf16 [Cout][32] = w/255 in (r,s,c) order, zero padded (tensor-core uint8 path)
+  __nv_bfloat16* w6 = nullptr;  // fp32-accurate mode: [Cout][k][k][6][Cin_eff] = planes hi|mid|lo|hi|mid|hi of the fp32 weight
   float* bias = nullptr;
   int cin = 0, cout = 0, k = 0, groups = 1;   // groups == 1 -> dense (possibly block-diagonal expansion)
 };
 
 static __nv_bfloat16 f2bf(float x) { return __float2bfloat16_rn(x); }
 
-struct T { __nv_bfloat16* p = nullptr; int cs = 0, co = 0, C = 0, H = 0, W = 0; bool image = false; };
+struct T { __nv_bfloat16* p = nullptr; int cs = 0, co = 0, C = 0, H = 0, W = 0; bool image = false; bool f32 = false; };   // f32: p is really float*
 
 struct Op {
-  enum Kind { GEMM, DIRECT, AVGPAD, AVGMAX, MAXPOOL5, UPSAMPLE, CBFUSE, LETTERBOX, STEM, STEM_IM2COL, DECODE, POST } kind;
+  enum Kind { GEMM, DIRECT, AVGPAD, AVGMAX, MAXPOOL5, UPSAMPLE, CBFUSE, LETTERBOX, STEM, STEM_IM2COL, DECODE, POST, SPLIT } kind;
   GemmLaunch gemm;
   DirectConvParams direct;
   TSlice s_in, s_out;
@@ -168,16 +169,17 @@ struct Op {
 
 struct YoloPlan {
   int B = 0, Hf = 0, Wf = 0, res = 0, is_f32 = 0, H = 0, W = 0, A = 0;
+  int Hr = 0, Wr = 0;          // the reference's letterboxed extent (H, W are it rounded up to a multiple of 32)
   std::vector<Op> ops;
-  std::vector<void*> allocs;
-  size_t alloc_bytes = 0;
+  size_t alloc_bytes = 0;      // bytes of the handle's shared workspace this plan addresses
+  uint64_t gen = 0;            // workspace generation the pointers / TMA descriptors were built against
+  uint64_t last_use = 0;       // LRU stamp
   float* pred = nullptr;   // [B,A,6]
   float* raw = nullptr;    // [B,84,A] (allocated lazily when a tap is requested)
   void* lb_out = nullptr;  // letterboxed frames (same dtype as input) or nullptr when identity
   double conv_flops = 0;
   int n_launch = 0;
   std::vector<T> layer_outs;   // per spec layer (parity taps)
-  ~YoloPlan() { for (void* p : allocs) cudaFree(p); }
 };
 
 struct YoloModel {
@@ -186,8 +188,14 @@ struct YoloModel {
   std::map<std::string, HostT> host;     // borrowed pointers, valid only during create
   std::map<std::string, ConvW> convs;
   std::vector<void*> allocs;
-  std::map<std::string, std::unique_ptr<YoloPlan>> plans;
+  std::map<std::string, std::unique_ptr<YoloPlan>> plans;   // bounded (kMaxPlans, least recently used goes first)
+  Arena arena;                 // activation workspace shared by all plans (size of the largest)
+  uint64_t tick = 0;
   int sms = 0;
+  // fp32-accurate mode (CC_YOLO_FP32_ACCURATE): activations are stored in fp32 and every conv runs on the same tcgen05 kernel
+  // over a 3-way bf16 split of both operands (six plane products, fp32 accumulation): the result carries fp32-level error
+  // instead of bf16's 2^-9, at ~6x the tensor work and 2x the activation bytes.  The mode the 1e-3 parity bar is checked in.
+  bool precise = false;
   ~YoloModel() { plans.clear(); for (void* p : allocs) cudaFree(p); }
 
   int upload(const void* h, size_t bytes, void** d) {
@@ -243,7 +251,34 @@ struct YoloModel {
         for (int kk = 0; kk < 27; ++kk) wt[static_cast<size_t>(co) * 32 + kk] = f2bf(wf[static_cast<size_t>(co) * 27 + kk] / 255.0f);
       if ((rc = upload(wt.data(), wt.size() * 2, reinterpret_cast<void**>(&cw.wtc)))) return rc;
     }
-    else { if ((rc = upload(w.data(), w.size() * 2, reinterpret_cast<void**>(&cw.w)))) return rc; }
+    else if (!precise) { if ((rc = upload(w.data(), w.size() * 2, reinterpret_cast<void**>(&cw.w)))) return rc; }
+    else {
+      // the fp32 weights again (w above is already rounded): planes [hi | mid | lo | hi | mid | hi] per filter tap, matching the
+      // activation planes [lo | mid | hi | mid | hi | hi] written by split_planes_kernel
+      std::vector<__nv_bfloat16> w6(w.size() * 6, f2bf(0.f));
+      int cb = 0;
+      for (size_t t = 0; t < names.size(); ++t) {
+        const float* src = host.find(names[t] + ".weight")->second.p;
+        const int cout = couts[t], cpg_out = cout / groups;
+        for (int co = 0; co < cout; ++co) {
+          const int g = co / cpg_out;
+          for (int ci = 0; ci < cin_g; ++ci)
+            for (int r = 0; r < k; ++r)
+              for (int s2 = 0; s2 < k; ++s2) {
+                const float v = src[((static_cast<size_t>(co) * cin_g + ci) * k + r) * k + s2];
+                const __nv_bfloat16 hi = f2bf(v);
+                const float r1 = v - __bfloat162float(hi);
+                const __nv_bfloat16 mid = f2bf(r1);
+                const __nv_bfloat16 lo = f2bf(r1 - __bfloat162float(mid));
+                const int ci_eff = dense ? g * cin_g + ci : ci;
+                __nv_bfloat16* d6 = &w6[(((static_cast<size_t>(cb + co) * k + r) * k + s2) * 6) * cin_eff + ci_eff];
+                d6[0] = hi; d6[cin_eff] = mid; d6[2 * cin_eff] = lo; d6[3 * cin_eff] = hi; d6[4 * cin_eff] = mid; d6[5 * cin_eff] = hi;
+              }
+        }
+        cb += cout;
+      }
+      if ((rc = upload(w6.data(), w6.size() * 2, reinterpret_cast<void**>(&cw.w6)))) return rc;
+    }
     if ((rc = upload(bias.data(), bias.size() * 4, reinterpret_cast<void**>(&cw.bias)))) return rc;
     convs[key] = cw;
     return CC_OK;
@@ -273,23 +308,26 @@ struct Builder {
   std::map<int, T> concat_buf;              // concat layer -> buffer
   std::vector<int> outC;                    // inferred channels per layer
 
+  Bump bump;                                // workspace carving; bump.dry = measuring pass (no launches are built)
+  size_t scratch_bytes = 0;                 // fp32-accurate mode: size of the plane-split scratch (from the measuring pass)
+  size_t max_scratch = 0;                   //   ... largest split any conv of this plan needs
+  __nv_bfloat16* scratch = nullptr;
+
   Builder(YoloModel& m, YoloPlan& p) : M(m), P(p) {}
 
   void* dalloc(size_t bytes) {
-    void* d = nullptr;
     if (rc) return nullptr;
-    if (cudaMalloc(&d, bytes) != cudaSuccess) { set_error("yolo plan: cudaMalloc(%zu) failed", bytes); rc = CC_ERR_CUDA; return nullptr; }
-    P.allocs.push_back(d);
-    P.alloc_bytes += bytes;
+    void* d = bump.take(bytes);
+    P.alloc_bytes = bump.off;
     return d;
   }
   T talloc(int C, int H, int W) {
-    T t; t.cs = C; t.co = 0; t.C = C; t.H = H; t.W = W;
-    t.p = static_cast<__nv_bfloat16*>(dalloc(static_cast<size_t>(P.B) * H * W * C * 2));
+    T t; t.cs = C; t.co = 0; t.C = C; t.H = H; t.W = W; t.f32 = M.precise;
+    t.p = static_cast<__nv_bfloat16*>(dalloc(static_cast<size_t>(P.B) * H * W * C * (M.precise ? 4 : 2)));
     return t;
   }
   static T slice(const T& t, int co, int C) { T s = t; s.co = t.co + co; s.C = C; return s; }
-  TSlice ts(const T& t) const { TSlice s; s.p = t.p; s.cs = t.cs; s.co = t.co; s.C = t.C; s.N = P.B; s.H = t.H; s.W = t.W; return s; }
+  TSlice ts(const T& t) const { TSlice s; s.p = t.p; s.cs = t.cs; s.co = t.co; s.C = t.C; s.N = P.B; s.H = t.H; s.W = t.W; s.f32 = t.f32 ? 1 : 0; return s; }
 
   // conv: in -> out slice (out.H/W must already be the conv's output extent)
   void conv(const std::string& key, const T& in, const T& out, int stride, int act, const T* res = nullptr,
@@ -299,9 +337,38 @@ struct Builder {
     if (it == M.convs.end()) { set_error("yolo plan: conv '%s' not loaded", key.c_str()); rc = CC_ERR_STATE; return; }
     const ConvW& cw = it->second;
     if (cw.cin != in.C) { set_error("yolo plan: conv '%s' expects Cin=%d, got %d", key.c_str(), cw.cin, in.C); rc = CC_ERR_INVALID; return; }
+    if (M.precise) {
+      if (!(cw.groups == 1 && tc_ok(cw.cin, cw.cout))) {
+        set_error("yolo plan: conv '%s' (%d->%d, groups %d) has no tensor-core form; the fp32-accurate mode needs one", key.c_str(), cw.cin, cw.cout, cw.groups);
+        rc = CC_ERR_INVALID;
+        return;
+      }
+      const size_t need = static_cast<size_t>(P.B) * in.H * in.W * 6 * in.C * 2;
+      if (need > max_scratch) max_scratch = need;
+    }
+    if (bump.dry) return;
     Op op;
     op.name = key;
-    if (cw.groups == 1 && tc_ok(cw.cin, cw.cout)) {
+    if (M.precise) {
+      // fp32 slice -> six bf16 planes in the scratch, then the same tcgen05 conv over 6*Cin channels with the plane-expanded
+      // weights, fp32 output, exact SiLU
+      Op sp; sp.kind = Op::SPLIT; sp.name = key + ".split"; sp.s_in = ts(in); sp.s_out = TSlice{}; sp.s_out.p = scratch;
+      P.ops.push_back(std::move(sp));
+      ConvDesc d{};
+      d.in = scratch; d.in_cs = 6 * in.C; d.in_co = 0; d.Cin = 6 * in.C;
+      d.N = P.B; d.Hin = in.H; d.Win = in.W; d.k = cw.k; d.stride = stride;
+      d.w = cw.w6; d.bias = cw.bias;
+      if (out_f32) { d.out = out_f32; d.out_cs = cw.cout; d.out_co = 0; }
+      else { d.out = out.p; d.out_cs = out.cs; d.out_co = out.co; }
+      d.out_f32 = 1;
+      d.Cout = cw.cout; d.act = act == CC_ACT_SILU ? ACT_SILU_EXACT : act;
+      if (res) { d.res = res->p; d.res_cs = res->cs; d.res_co = res->co; }
+      op.kind = Op::GEMM;
+      rc = conv_gemm_build(d, M.sms, &op.gemm);
+      if (rc) return;
+      op.gemm.flops /= 6.0;                      // algorithmic FLOPs of the conv, not of the six plane products
+      P.conv_flops += op.gemm.flops;
+    } else if (cw.groups == 1 && tc_ok(cw.cin, cw.cout)) {
       ConvDesc d{};
       d.in = in.p; d.in_cs = in.cs; d.in_co = in.co; d.Cin = in.C;
       d.N = P.B; d.Hin = in.H; d.Win = in.W; d.k = cw.k; d.stride = stride;
@@ -333,7 +400,7 @@ struct Builder {
     P.ops.push_back(std::move(op));
   }
   void simple(Op::Kind kind, const T& in, const T& out, const char* name) {
-    if (rc) return;
+    if (rc || bump.dry) return;
     Op op; op.kind = kind; op.s_in = ts(in); op.s_out = ts(out); op.name = name;
     P.ops.push_back(std::move(op));
   }
@@ -407,13 +474,22 @@ int Builder::build() {
   if (dh < 0) dh += 32;
   dw /= 2; dh /= 2;
   const int px = int(std::nearbyint(dw - 0.1)), py = int(std::nearbyint(dh - 0.1));
-  P.H = new_h + 2 * py; P.W = new_w + 2 * px;
-  CC_REQUIRE(P.H % 32 == 0 && P.W % 32 == 0 && P.H > 0 && P.W > 0,
-             "yolo: letterboxed input %dx%d is not a multiple of 32 (frame %dx%d, res %d)", P.H, P.W, P.Hf, P.Wf, P.res);
+  // The reference pads int(round(d - 0.1)) on BOTH sides, so when (res - new) % 32 is odd its net input is one pixel short of
+  // a multiple of 32 — and it keeps going: a 3x3/s2/p1 conv over 2k-1 rows gives the same k output rows as
+  // over 2k rows whose last row is zero.  So the net input buffer is rounded up to the multiple of 32 with that zero row /
+  // column (the letterbox kernel pads with zeros anyway): identical arithmetic, even dims for the TMA views.  scale_boxes
+  // still sees the reference's odd extent (Hr, Wr below).
+  const int Hr = new_h + 2 * py, Wr = new_w + 2 * px;
+  P.H = (Hr + 31) / 32 * 32; P.W = (Wr + 31) / 32 * 32;
+  P.Hr = Hr; P.Wr = Wr;
+  CC_REQUIRE(P.H > 0 && P.W > 0 && P.H - Hr <= 1 && P.W - Wr <= 1,
+             "yolo: letterboxed input %dx%d is not within one pixel of a multiple of 32 (frame %dx%d, res %d)", Hr, Wr, P.Hf, P.Wf, P.res);
   const void* net_in = nullptr;   // filled per run when identity (frames pointer) -> patched in run()
-  if (!(new_w == P.Wf && new_h == P.Hf && px == 0 && py == 0)) {
+  if (!(new_w == P.Wf && new_h == P.Hf && px == 0 && py == 0 && P.H == Hr && P.W == Wr)) {
     const size_t es = P.is_f32 ? 4 : 1;
     P.lb_out = dalloc(static_cast<size_t>(P.B) * P.H * P.W * 3 * es);
+    net_in = P.lb_out;
+    if (!bump.dry) {
     Op op; op.kind = Op::LETTERBOX; op.name = "letterbox";
     op.lb = LetterboxParams{};
     op.lb.in = nullptr; op.lb.out = P.lb_out; op.lb.is_f32 = P.is_f32;
@@ -421,8 +497,10 @@ int Builder::build() {
     op.lb.pad_y = py; op.lb.pad_x = px; op.lb.Hout = P.H; op.lb.Wout = P.W;
     op.lb.sx = float(double(P.Wf) / double(new_w)); op.lb.sy = float(double(P.Hf) / double(new_h));
     P.ops.push_back(std::move(op));
-    net_in = P.lb_out;
+    }
   }
+
+  if (M.precise && !bump.dry) scratch = static_cast<__nv_bfloat16*>(dalloc(scratch_bytes));
 
   outs.assign(nl, T{});
   cbl_chunks.assign(nl, {});
@@ -442,11 +520,12 @@ int Builder::build() {
           out = out_for(i, l.b, in.H / 2, in.W / 2);
           const ConvW& cw = M.convs[pfx];
           static const int stem_tc_env = getenv("CC_STEM_TC") ? atoi(getenv("CC_STEM_TC")) : 1;
-          if (!P.is_f32 && stem_tc_env && cw.cout % 16 == 0) {
+          if (!P.is_f32 && stem_tc_env && cw.cout % 16 == 0 && !M.precise) {
             // uint8 frames: raw pixel values are exact in bf16 -> im2col to [B*Ho*Wo, 32] and run the tensor-core GEMM
             // with weights bf16(w/255)
             const long long Mrows = static_cast<long long>(P.B) * (P.H / 2) * (P.W / 2);
             __nv_bfloat16* cols = static_cast<__nv_bfloat16*>(dalloc(static_cast<size_t>(Mrows) * 32 * 2));
+            if (bump.dry) break;
             { Op op; op.kind = Op::STEM_IM2COL; op.name = pfx + ".im2col"; op.stem = StemParams{};
               op.stem.in = net_in; op.stem.B = P.B; op.stem.H = P.H; op.stem.W = P.W;
               op.s_out.p = cols; P.ops.push_back(std::move(op)); }
@@ -463,6 +542,7 @@ int Builder::build() {
             P.ops.push_back(std::move(op));
             break;
           }
+          if (bump.dry) break;
           Op op; op.kind = Op::STEM; op.name = pfx;
           op.stem = StemParams{};
           op.stem.in = net_in; op.stem.is_f32 = P.is_f32; op.stem.B = P.B; op.stem.H = P.H; op.stem.W = P.W;
@@ -554,6 +634,7 @@ int Builder::build() {
         // detection/yolov9.py:230-245
         const T& last = src(l.f.back());
         out = out_for(i, last.C, last.H, last.W);
+        if (bump.dry) break;
         Op op; op.kind = Op::CBFUSE; op.name = pfx;
         op.cbf = CBFuseParams{};
         op.cbf.nsrc = static_cast<int>(l.f.size()) - 1;
@@ -598,13 +679,15 @@ int Builder::build() {
         P.A = A;
         P.pred = static_cast<float*>(dalloc(static_cast<size_t>(P.B) * A * 6 * 4));
         dec.dec.B = P.B; dec.dec.A = A; dec.dec.conf_thr = 0.25f; dec.dec.pred = P.pred; dec.dec.raw = nullptr;
+        if (bump.dry) break;
         P.ops.push_back(std::move(dec));
         Op po; po.kind = Op::POST; po.name = "postprocess";
         po.post = PostParams{};
         po.post.pred = P.pred; po.post.B = P.B; po.post.A = A; po.post.max_det = 300; po.post.iou_thr = 0.45f;
-        const double gain = std::min(double(P.H) / P.Hf, double(P.W) / P.Wf);
+        const int Hr = P.Hr, Wr = P.Wr;               // the reference's img1_shape (detection/yolov9.py:406-416)
+        const double gain = std::min(double(Hr) / P.Hf, double(Wr) / P.Wf);
         po.post.gain = float(gain);
-        po.post.pad_x = float((P.W - P.Wf * gain) / 2); po.post.pad_y = float((P.H - P.Hf * gain) / 2);
+        po.post.pad_x = float((Wr - P.Wf * gain) / 2); po.post.pad_y = float((Hr - P.Hf * gain) / 2);
         po.post.clip_w = float(P.Wf); po.post.clip_h = float(P.Hf); po.post.do_scale = 1;
         po.post.out = nullptr;
         P.ops.push_back(std::move(po));
@@ -619,13 +702,16 @@ int Builder::build() {
 }
 
 static int plan_run(YoloPlan& P, const void* d_frames, float* d_out, float* d_raw, cudaStream_t st,
-                    std::vector<cudaEvent_t>* ev = nullptr) {
-  size_t oi = 0;
+                    std::vector<cudaEvent_t>* ev = nullptr, unsigned long long* d_trace = nullptr) {
+  size_t oi = 0, ti = 0;
   for (Op& op : P.ops) {
     int rc = CC_OK;
     if (ev) cudaEventRecord((*ev)[oi++], st);
     switch (op.kind) {
-      case Op::GEMM: rc = conv_gemm_launch(op.gemm, st); break;
+      case Op::GEMM:
+        if (d_trace) { GemmLaunch g = op.gemm; g.p.trace = d_trace + 3 * ti; rc = conv_gemm_launch(g, st); }
+        else rc = conv_gemm_launch(op.gemm, st);
+        break;
       case Op::DIRECT: rc = conv_direct_launch(op.direct, st); break;
       case Op::AVGPAD: rc = avgpool2_pad_launch(op.s_in, op.s_out, st); break;
       case Op::AVGMAX: rc = avgmax_pool_launch(op.s_in, op.s_out, st); break;
@@ -640,8 +726,10 @@ static int plan_run(YoloPlan& P, const void* d_frames, float* d_out, float* d_ra
         break;
       case Op::DECODE: { DecodeParams q = op.dec; q.raw = d_raw; rc = decode_launch(q, st); break; }
       case Op::POST: { PostParams q = op.post; q.out = d_out; rc = postprocess_launch(q, st); break; }
+      case Op::SPLIT: rc = split_planes_launch(op.s_in, op.s_out.p, st); break;
     }
     if (rc) return rc;
+    ++ti;
   }
   if (ev) cudaEventRecord((*ev)[oi], st);
   return CC_OK;
@@ -652,7 +740,7 @@ static const char* op_kind_name(Op::Kind k) {
     case Op::GEMM: return "conv_gemm"; case Op::DIRECT: return "conv_direct"; case Op::AVGPAD: return "avgpool2_pad";
     case Op::AVGMAX: return "avgmax_pool"; case Op::MAXPOOL5: return "maxpool5"; case Op::UPSAMPLE: return "upsample2";
     case Op::CBFUSE: return "cbfuse"; case Op::LETTERBOX: return "letterbox"; case Op::STEM: return "stem"; case Op::STEM_IM2COL: return "stem_im2col";
-    case Op::DECODE: return "decode"; case Op::POST: return "postprocess";
+    case Op::DECODE: return "decode"; case Op::POST: return "postprocess"; case Op::SPLIT: return "split_planes";
   }
   return "?";
 }
@@ -667,13 +755,20 @@ extern "C" {
 
 int cc_yolo_create(const char* size, int n_tensors, const char* const* names, const float* const* h_data,
                    const int64_t* numels, cc_yolo** out) {
+  return cc_yolo_create_ex(size, 0, n_tensors, names, h_data, numels, out);
+}
+
+int cc_yolo_create_ex(const char* size, int flags, int n_tensors, const char* const* names, const float* const* h_data,
+                      const int64_t* numels, cc_yolo** out) {
   CC_REQUIRE(size && out, "cc_yolo_create: null argument");
+  CC_REQUIRE((flags & ~CC_YOLO_FP32_ACCURATE) == 0, "cc_yolo_create_ex: unknown flags 0x%x", flags);
   const int sms = device_sm_count();
   CC_REQUIRE(sms > 0, "cc_yolo_create: no sm_100 (B200) device");
   std::unique_ptr<cc_yolo> h(new cc_yolo());
   YoloModel& M = h->m;
   M.size = size;
   M.sms = sms;
+  M.precise = (flags & CC_YOLO_FP32_ACCURATE) != 0;
   CC_REQUIRE(build_spec(M.size, &M.spec), "cc_yolo_create: unknown size '%s' (t|s|m|c|e)", size);
   for (int i = 0; i < n_tensors; ++i) M.host[names[i]] = HostT{h_data[i], static_cast<long long>(numels[i])};
 
@@ -758,20 +853,72 @@ int cc_yolo_destroy(cc_yolo* h) {
   return CC_OK;
 }
 
-static int get_plan(cc_yolo* h, int is_f32, int B, int Hf, int Wf, int res, YoloPlan** out) {
+static constexpr size_t kMaxPlans = 16;   // cached plans per handle (host metadata only: plans own no device memory)
+
+static std::string plan_key(int is_f32, int B, int Hf, int Wf, int res) {
   char key[96];
   snprintf(key, sizeof(key), "%d,%d,%d,%d,%d", is_f32, B, Hf, Wf, res);
-  auto it = h->m.plans.find(key);
-  if (it == h->m.plans.end()) {
-    std::unique_ptr<YoloPlan> P(new YoloPlan());
-    P->B = B; P->Hf = Hf; P->Wf = Wf; P->res = res; P->is_f32 = is_f32;
-    Builder bld(h->m, *P);
-    int rc = bld.build();
-    if (rc) return rc;
-    it = h->m.plans.emplace(key, std::move(P)).first;
-  }
-  *out = it->second.get();
+  return key;
+}
+// workspace bytes a plan of this shape addresses (measuring pass of the builder: no device work)
+static int plan_bytes(cc_yolo* h, int is_f32, int B, int Hf, int Wf, int res, size_t* bytes, size_t* scratch = nullptr) {
+  YoloPlan tmp;
+  tmp.B = B; tmp.Hf = Hf; tmp.Wf = Wf; tmp.res = res; tmp.is_f32 = is_f32;
+  Builder dry(h->m, tmp);
+  dry.bump.dry = true;
+  int rc = dry.build();
+  if (rc) return rc;
+  *bytes = dry.bump.off + dry.max_scratch + 4096;
+  if (scratch) *scratch = dry.max_scratch;
   return CC_OK;
+}
+static int get_plan(cc_yolo* h, int is_f32, int B, int Hf, int Wf, int res, YoloPlan** out) {
+  YoloModel& M = h->m;
+  const std::string key = plan_key(is_f32, B, Hf, Wf, res);
+  auto it = M.plans.find(key);
+  if (it != M.plans.end() && it->second->gen == M.arena.gen) {
+    it->second->last_use = ++M.tick;
+    *out = it->second.get();
+    return CC_OK;
+  }
+  size_t bytes = 0, scratch = 0;
+  int rc = plan_bytes(h, is_f32, B, Hf, Wf, res, &bytes, &scratch);
+  if (rc) return rc;
+  if ((rc = M.arena.reserve(bytes))) return rc;
+  // plans built against an older workspace are stale (they are rebuilt on their next use)
+  for (auto p = M.plans.begin(); p != M.plans.end();)
+    p = (p->second->gen != M.arena.gen) ? M.plans.erase(p) : std::next(p);
+  std::unique_ptr<YoloPlan> P(new YoloPlan());
+  P->B = B; P->Hf = Hf; P->Wf = Wf; P->res = res; P->is_f32 = is_f32;
+  Builder bld(M, *P);
+  bld.bump.base = static_cast<uint8_t*>(M.arena.base);
+  bld.scratch_bytes = scratch;
+  rc = bld.build();
+  if (rc) return rc;
+  CC_REQUIRE(bld.bump.off <= M.arena.cap, "yolo plan: workspace overrun (%zu > %zu)", bld.bump.off, M.arena.cap);
+  P->gen = M.arena.gen;
+  P->last_use = ++M.tick;
+  if (M.plans.size() >= kMaxPlans) {
+    auto lru = M.plans.begin();
+    for (auto p = M.plans.begin(); p != M.plans.end(); ++p)
+      if (p->second->last_use < lru->second->last_use) lru = p;
+    M.plans.erase(lru);
+  }
+  *out = (M.plans[key] = std::move(P)).get();
+  return CC_OK;
+}
+
+int cc_yolo_workspace_bytes(cc_yolo* h, int is_f32, int B, int Hf, int Wf, int res, size_t* bytes) {
+  CC_REQUIRE(h && bytes && B > 0 && Hf > 0 && Wf > 0 && res > 0, "cc_yolo_workspace_bytes: bad argument");
+  return plan_bytes(h, is_f32, B, Hf, Wf, res, bytes);
+}
+
+int cc_yolo_set_workspace(cc_yolo* h, void* d_workspace, size_t bytes) {
+  CC_REQUIRE(h, "cc_yolo_set_workspace: null handle");
+  CC_REQUIRE(d_workspace == nullptr || (reinterpret_cast<uintptr_t>(d_workspace) & 255) == 0,
+             "cc_yolo_set_workspace: the workspace must be 256-byte aligned");
+  h->m.plans.clear();
+  return h->m.arena.adopt(d_workspace, bytes);
 }
 
 int cc_yolo_forward(cc_yolo* h, const void* d_frames, int is_f32, int B, int Hf, int Wf, int res, float* d_out,
@@ -829,14 +976,47 @@ int cc_yolo_profile(cc_yolo* h, const void* d_frames, int is_f32, int B, int Hf,
   return rc;
 }
 
+/* In-situ device timeline of one forward (no events between the launches, so programmatic dependent launch overlaps
+ * as in production): for every conv_gemm op, globaltimer ns of (first CTA entered, grid dependency released, last CTA
+ * exited); zeros for the other ops.  host_ns: [3 * cap].  Synchronises at the end. */
+int cc_yolo_trace(cc_yolo* h, const void* d_frames, int is_f32, int B, int Hf, int Wf, int res, float* d_out, int cap,
+                  unsigned long long* host_ns, const char** kinds, const char** names, double* flops, int* n_ops, void* stream) {
+  CC_REQUIRE(h && d_frames && d_out && host_ns, "cc_yolo_trace: bad argument");
+  YoloPlan* P = nullptr;
+  int rc = get_plan(h, is_f32, B, Hf, Wf, res, &P);
+  if (rc) return rc;
+  const size_t n = P->ops.size();
+  unsigned long long* d_trace = nullptr;
+  CC_CHECK_CUDA(cudaMalloc(&d_trace, n * 3 * sizeof(unsigned long long)));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaMemsetAsync(d_trace, 0, n * 3 * sizeof(unsigned long long), st);
+  rc = plan_run(*P, d_frames, d_out, nullptr, st, nullptr, d_trace);
+  if (!rc) {
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) {
+      const size_t m = n < static_cast<size_t>(cap) ? n : static_cast<size_t>(cap);
+      e = cudaMemcpy(host_ns, d_trace, m * 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+      for (size_t i = 0; i < m; ++i) {
+        if (kinds) kinds[i] = op_kind_name(P->ops[i].kind);
+        if (names) names[i] = P->ops[i].name.c_str();
+        if (flops) flops[i] = P->ops[i].kind == Op::GEMM ? P->ops[i].gemm.flops : 0.0;
+      }
+    }
+    if (e != cudaSuccess) { set_error("cc_yolo_trace: %s", cudaGetErrorString(e)); rc = CC_ERR_CUDA; }
+  }
+  cudaFree(d_trace);
+  if (n_ops) *n_ops = static_cast<int>(n);
+  return rc;
+}
+
 // parity tap: copy the output of spec layer `layer` of the cached plan (after a forward) to dense fp32 NHWC
-__global__ void tap_kernel(const __nv_bfloat16* src, int cs, int co, int C, long long npix, float* dst) {
+__global__ void tap_kernel(const __nv_bfloat16* src, int f32, int cs, int co, int C, long long npix, float* dst) {
   const long long total = npix * C;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long pix = i / C;
     const int c = static_cast<int>(i % C);
-    dst[i] = __bfloat162float(src[pix * cs + co + c]);
+    dst[i] = f32 ? reinterpret_cast<const float*>(src)[pix * cs + co + c] : __bfloat162float(src[pix * cs + co + c]);
   }
 }
 
@@ -853,7 +1033,7 @@ int cc_yolo_layer_output(cc_yolo* h, int is_f32, int B, int Hf, int Wf, int res,
   if (W) *W = t.W;
   if (!d_dst || t.image || !t.p) return CC_OK;
   const long long npix = static_cast<long long>(B) * t.H * t.W;
-  tap_kernel<<<148 * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(t.p, t.cs, t.co, t.C, npix, d_dst);
+  tap_kernel<<<148 * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(t.p, t.f32 ? 1 : 0, t.cs, t.co, t.C, npix, d_dst);
   CC_CHECK_CUDA(cudaGetLastError());
   return CC_OK;
 }

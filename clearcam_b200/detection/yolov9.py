@@ -129,10 +129,13 @@ def postprocess(output, max_det=300, conf_threshold=0.25, iou_threshold=0.45):
 class YOLOv9:
     """YOLOv9(size, res) — same constructor/call contract as the reference (detection/yolov9.py:298-388)."""
 
-    def __init__(self, size: str = "t", res: int = 1280, weights=None, pad: bool = True):
+    def __init__(self, size: str = "t", res: int = 1280, weights=None, pad: bool = True, precise: bool = False):
         """pad=False keeps a size with odd widths (t) on its literal graph, whose narrow convs then take the generic
-        CUDA-core kernel; m only runs padded."""
-        self.size, self.res, self.pad = size, res, pad
+        CUDA-core kernel; m only runs padded.
+        precise=True: the fp32-accurate mode (CC_YOLO_FP32_ACCURATE) — fp32 activations, every conv as six bf16 plane
+        products on the tensor cores with fp32 accumulation, exact SiLU.  The reference is fp32 end to end; this is the
+        mode that reproduces its boxes / scores at the north-star tolerance (the default stores activations in bf16)."""
+        self.size, self.res, self.pad, self.precise = size, res, pad, bool(precise)
         self._h = None
         if weights is None:
             weights = safe_load(fetch(f"https://huggingface.co/roryclear/yolov9/resolve/main/yolov9-{size}.safetensors"))
@@ -157,7 +160,8 @@ class YOLOv9:
         ptrs = (ctypes.c_void_p * len(items))(*[a.ctypes.data for _, a in items])
         nums = (ctypes.c_int64 * len(items))(*[a.size for _, a in items])
         h = ctypes.c_void_p()
-        check(L.cc_yolo_create(lib_size.encode(), len(items), names, ptrs, nums, ctypes.byref(h)), "cc_yolo_create")
+        check(L.cc_yolo_create_ex(lib_size.encode(), 1 if self.precise else 0, len(items), names, ptrs, nums, ctypes.byref(h)),
+              "cc_yolo_create_ex")
         if self._h is not None:
             L.cc_yolo_destroy(self._h)
         self._h = h
@@ -278,6 +282,25 @@ class YOLOv9:
                                     ms, fl, by, kinds, names, ctypes.byref(n), stream_ptr()), "cc_yolo_profile")
         return [{"kind": kinds[i].decode(), "name": names[i].decode(), "ms": ms[i], "flops": fl[i], "bytes": by[i]}
                 for i in range(n.value)]
+
+    def trace(self, frames):
+        """In-situ device timeline of one forward (no events between launches): list of dicts {kind, name, flops,
+        t_in, t_dep, t_out} in ns relative to the first kernel (zeros for the non-GEMM kernels)."""
+        t = self._as_device_frames(frames)
+        B, Hf, Wf, _ = t.shape
+        out = torch.empty(B, 300, 6, device="cuda", dtype=torch.float32)
+        cap = 1024
+        ns = (ctypes.c_ulonglong * (3 * cap))()
+        fl = (ctypes.c_double * cap)()
+        kinds = (ctypes.c_char_p * cap)()
+        names = (ctypes.c_char_p * cap)()
+        n = ctypes.c_int()
+        check(lib().cc_yolo_trace(self._h, ptr(t), 1 if t.dtype == torch.float32 else 0, B, Hf, Wf, self.res, ptr(out), cap,
+                                  ns, kinds, names, fl, ctypes.byref(n), stream_ptr()), "cc_yolo_trace")
+        t0 = min(ns[3 * i] for i in range(n.value) if ns[3 * i])
+        rel = lambda v: (v - t0) if v else 0
+        return [{"kind": kinds[i].decode(), "name": names[i].decode(), "flops": fl[i], "t_in": rel(ns[3 * i]),
+                 "t_dep": rel(ns[3 * i + 1]), "t_out": rel(ns[3 * i + 2])} for i in range(n.value)]
 
     def layer_output(self, layer: int, B, Hf, Wf, is_f32=False):
         """Parity tap: output of graph layer `layer` of the last forward with this shape, as fp32 (B,C,H,W), or None."""

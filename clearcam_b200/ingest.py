@@ -63,27 +63,62 @@ class PipeReader(threading.Thread):
         super().__init__(daemon=True, name=f"ingest-{name}")
         self.mailbox, self.open_stream, self.max_fail, self.retry_sleep = mailbox, open_stream, max_fail, retry_sleep
         self.restarts = 0
+        self.open_errors = 0                   # failed open_stream() calls (camera / ffmpeg down): retried with back-off
+        self.last_error: Optional[BaseException] = None
+        self._stream = None
         self._stop_evt = threading.Event()
 
     def stop(self):
+        """Ask the thread to end and close the stream so a read blocked on a silent camera returns."""
         self._stop_evt.set()
+        self._close()
 
-    def run(self):
-        stream, fails = self.open_stream(), 0
+    def _close(self):
+        s, self._stream = self._stream, None
+        if s is not None:
+            try:
+                s.close()
+            except Exception:
+                pass
+
+    def _open(self) -> bool:
+        """open_stream() under supervision: a camera or ffmpeg that is down must not kill the reader thread (the reference's
+        frame_loop keeps logging and retrying, clearcam.py:401-421).  Back-off doubles up to 8x retry_sleep."""
+        delay = self.retry_sleep
         while not self._stop_evt.is_set():
             try:
-                ok = self.mailbox.fill(stream)
-            except Exception:                                   # clearcam.py:420-421: log-and-retry supervision
-                ok = False
-            if ok:
-                fails = 0
-                continue
-            fails += 1
-            if fails > self.max_fail:                           # clearcam.py:408-411: restart the stream
+                self._stream = self.open_stream()
+                return True
+            except Exception as ex:
+                self.open_errors += 1
+                self.last_error = ex
+                self._stop_evt.wait(delay)
+                delay = min(delay * 2, self.retry_sleep * 8)
+        return False
+
+    def run(self):
+        fails = 0
+        try:
+            if not self._open():
+                return
+            while not self._stop_evt.is_set():
                 try:
-                    stream.close()
-                except Exception:
-                    pass
-                stream, fails = self.open_stream(), 0
-                self.restarts += 1
-            self._stop_evt.wait(self.retry_sleep)
+                    ok = self.mailbox.fill(self._stream)
+                except Exception as ex:                             # clearcam.py:420-421: log-and-retry supervision
+                    self.last_error = ex
+                    ok = False
+                if ok:
+                    fails = 0
+                    continue
+                if self._stop_evt.is_set():
+                    break
+                fails += 1
+                if fails > self.max_fail:                           # clearcam.py:408-411: restart the stream
+                    self._close()
+                    if not self._open():
+                        break
+                    fails = 0
+                    self.restarts += 1
+                self._stop_evt.wait(self.retry_sleep)
+        finally:
+            self._close()

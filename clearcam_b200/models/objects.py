@@ -27,6 +27,7 @@ import torch
 from .._lib import CCError, check, lib, ptr, stream_ptr
 from ..detection.yolov9 import DeviceResult, _to_host_fp32, fetch, safe_load
 from ..utils.clip_tokenizer import SimpleTokenizer
+from ..utils.helpers import batch_bucket
 
 # (image_size, patch, v_width, v_layers, v_heads, v_mlp, embed_dim, t_width, t_layers, t_heads, t_mlp, vocab, ctx)
 ARCHS = {
@@ -187,7 +188,8 @@ class ObjectFinder:
         self.clip = False
         self.face = False
         self.jit_cache = {}
-        self._index = None            # (paths, device tensor [N,D]) cache of image_embeddings
+        self._index = None            # (paths, device tensor [N,D], per-row search metadata) cache of image_embeddings
+        self._index_fp = ()           # identities of the cached values
         self.model: Optional[OpenCLIP] = None
 
     def init_clip(self, weights=None, arch: str = "ViT-L/14"):
@@ -239,7 +241,7 @@ class ObjectFinder:
             return None
         return nx1, ny1, nx2, ny2
 
-    def preprocess_device(self, frames, rects, bgr: bool = True, size: Optional[int] = None):
+    def preprocess_device(self, frames, rects, bgr: bool = True, size: Optional[int] = None, rows: Optional[int] = None):
         """frames: uint8 [n,H,W,3] or [H,W,3] (host or device; BGR as the cameras deliver them), rects: K rows of
         (frame, x1, y1, x2, y2) or (x1, y1, x2, y2) -> DeviceResult (K,3,S,S) float32, bit-identical to
         `preprocess(cv2.cvtColor(frame[y1:y2, x1:x2], BGR2RGB))` with OpenCV's own bicubic — without leaving the GPU."""
@@ -256,7 +258,9 @@ class ObjectFinder:
             r = np.concatenate([np.zeros((len(r), 1), np.int32), r], 1)
         r = np.ascontiguousarray(r, np.int32)
         s = size or (self.model.image_size if self.model is not None else 224)
-        out = torch.empty(len(r), 3, s, s, device="cuda", dtype=torch.float32)
+        # rows > K: the result is allocated with `rows` images, the first K filled and the rest zero (batch padding)
+        out = torch.empty(len(r), 3, s, s, device="cuda", dtype=torch.float32) if not rows or rows <= len(r) else \
+            torch.zeros(rows, 3, s, s, device="cuda", dtype=torch.float32)
         check(lib().cc_clip_preprocess(ptr(t), t.shape[0], t.shape[1], t.shape[2], r.ctypes.data, len(r), s, int(bgr), ptr(out),
                                        stream_ptr(None)), "cc_clip_preprocess")
         return DeviceResult(out)
@@ -264,19 +268,49 @@ class ObjectFinder:
     def embed_crops(self, frames, rects, bgr: bool = True):
         """Detector frame -> embeddings of its objects in one device pass: crop + preprocess + `precompute_embedding`
         (the reference goes through cv2.imwrite / cv2.imread and the host, clearcam.py:398, 274-276)."""
-        return self.model.precompute_embedding(self.preprocess_device(frames, rects, bgr))
+        k = len(rects)
+        if k == 0:
+            return DeviceResult(torch.empty(0, self.model.embed_dim, device="cuda", dtype=torch.float32))
+        # the number of objects differs from frame to frame: pad the batch to a bucket size so the encoder keeps a small,
+        # bounded set of plans; the padded rows are dropped
+        x = self.preprocess_device(frames, rects, bgr, rows=batch_bucket(k))
+        return DeviceResult(self.model.precompute_embedding(x).tensor[:k])
 
     def _device_index(self):
+        """Contiguous device copy of `image_embeddings` plus, per row, what `search` filters and groups on — rebuilt
+        whenever a key OR the array stored under a key changes (the fingerprint holds the identity of every value, so an
+        embedding replaced under an existing path is seen).  Returns (paths, device [N,D], meta)."""
         keys = [k for k, v in self.image_embeddings.items() if v is not None]
-        if self._index is None or self._index[0] != keys:
+        fp = tuple(id(self.image_embeddings[k]) for k in keys)
+        if self._index is None or self._index[0] != keys or self._index_fp != fp:
+            self._index_fp = fp
             mat = np.concatenate([np.asarray(self.image_embeddings[k], np.float32).reshape(1, -1) for k in keys]) if keys \
                 else np.zeros((0, self.model.embed_dim if self.model else 1), np.float32)
-            self._index = (keys, torch.from_numpy(mat).cuda())
+            n = len(keys)
+            norm = np.array([k.replace("\\", "/") for k in keys], dtype=str) if n else np.zeros(0, dtype=str)
+            jpg = np.zeros(n, bool)
+            truthy = np.zeros(n, bool)
+            group = np.arange(n, dtype=np.int32)             # a row without an object id is its own group
+            first = {}
+            for i, k in enumerate(keys):
+                filename = os.path.basename(k)
+                if not filename.lower().endswith(".jpg"):     # models/objects.py:370: only .jpg rows are candidates
+                    continue
+                jpg[i] = True
+                oid = event_img_info(filename.split(".jpg")[0])["object_id"] if "_" in filename else None
+                if oid is not None:
+                    group[i] = first.setdefault(oid, i)       # group id = first row of that object id
+                    truthy[i] = bool(oid)
+            meta = {"norm": norm, "jpg": jpg, "truthy": truthy, "group": torch.from_numpy(group).cuda(),
+                    "ident": torch.arange(n, dtype=torch.int32, device="cuda"),
+                    "work": torch.empty(max(n, 1), dtype=torch.int64, device="cuda")}
+            self._index = (keys, torch.from_numpy(mat).cuda(), meta)
         return self._index
 
     def search(self, query=None, top_k=10, cam_name=None, timestamp=None, text_embedding=None, is_face=False):
-        """models/objects.py:356-390, same filtering / best-per-object-id / ordering; the N dot products run as one
-        device pass over the contiguous index instead of a Python loop."""
+        """models/objects.py:356-390 — same filtering, best score per object id, descending order, top_k — with the N dot
+        products, the per-object maximum and the top-k selection in one device pass over the contiguous index
+        (cc_search_topk): only the k winners come back over PCIe.  (An exact score tie goes to the earlier index row.)"""
         if is_face:
             raise CCError("face search is outside the hot path built here")
         if not self.image_embeddings:
@@ -284,29 +318,26 @@ class ObjectFinder:
             return []
         if text_embedding is None:
             text_embedding = self.model._encode_text(query).numpy()
-        keys, index = self._device_index()
-        scores = search_scores(index, np.asarray(text_embedding, np.float32).reshape(1, -1))[0].cpu().numpy()
-        sims = []
-        for path, similarity in zip(keys, scores):
-            norm = path.replace("\\", "/")
-            if cam_name and f"/cameras/{cam_name}/" not in norm:
-                continue
-            if timestamp and f"/objects/{timestamp}/" not in norm and "/objects/video/" not in norm:
-                continue
-            filename = os.path.basename(path)
-            if filename.lower().endswith(".jpg"):
-                oid = event_img_info(filename.split(".jpg")[0])["object_id"] if "_" in filename else None
-                sims.append((path, float(similarity), oid))
-        if any(s[2] for s in sims):
-            best = {}
-            for path, score, oid in sims:
-                if oid is not None and (oid not in best or score > best[oid][1]):
-                    best[oid] = (path, score)
-            results = list(best.values()) + [(p, s) for p, s, oid in sims if oid is None]
-        else:
-            results = [(p, s) for p, s, _ in sims]
-        results.sort(key=lambda x: x[1], reverse=True)
-        return results[:top_k]
+        keys, index, meta = self._device_index()
+        n = len(keys)
+        if n == 0 or top_k <= 0:
+            return []
+        mask = meta["jpg"]
+        if cam_name:
+            mask = mask & (np.char.find(meta["norm"], f"/cameras/{cam_name}/") >= 0)
+        if timestamp:
+            mask = mask & ((np.char.find(meta["norm"], f"/objects/{timestamp}/") >= 0) | (np.char.find(meta["norm"], "/objects/video/") >= 0))
+        # the reference groups by object id only when some candidate has a (non-empty) one (:377)
+        group = meta["group"] if bool((meta["truthy"] & mask).any()) else meta["ident"]
+        dmask = None if bool(mask.all()) else torch.from_numpy(np.ascontiguousarray(mask.astype(np.uint8))).cuda()
+        q = torch.from_numpy(np.ascontiguousarray(np.asarray(text_embedding, np.float32).reshape(-1))).cuda()
+        k = int(min(top_k, n))
+        rows = torch.empty(k, dtype=torch.int32, device="cuda")
+        scores = torch.empty(k, dtype=torch.float32, device="cuda")
+        check(lib().cc_search_topk(ptr(index), n, index.shape[1], ptr(q), ptr(group), ptr(dmask), n, k, ptr(meta["work"]), ptr(rows),
+                                   ptr(scores), stream_ptr()), "cc_search_topk")
+        rows, scores = rows.cpu().numpy(), scores.cpu().numpy()
+        return [(keys[r], float(sc)) for r, sc in zip(rows, scores) if r >= 0]
 
     def _load_all_embeddings(self, face=False):
         """models/objects.py:392-421: merge every <cam>/objects/<date>/embeddings.pkl into image_embeddings."""

@@ -10,3 +10,14 @@ def jit_infer(fn, x, jit_cache):
     reference's dict does."""
     jit_cache.setdefault(tuple(x.shape), True)
     return fn(x)
+
+
+def batch_bucket(n: int) -> int:
+    """Batch sizes the library is called with when the caller's count varies from step to step (cameras that delivered a
+    new frame, objects cropped out of a frame): every distinct batch size is a distinct cached plan (the reference's
+    TinyJit would likewise capture one graph per shape, :214-221), so counts are padded up to 1, 2, 4, 8, 12, 16, 24, 32,
+    then multiples of 16 — at most a third of padding, and a bounded set of plans."""
+    for b in (1, 2, 4, 8, 12, 16, 24, 32):
+        if n <= b:
+            return b
+    return (n + 15) // 16 * 16

@@ -59,6 +59,13 @@ typedef struct cc_yolo cc_yolo;
  * layout and uploaded once; the host pointers are not retained. */
 int cc_yolo_create(const char* size, int n_tensors, const char* const* names, const float* const* h_data,
                    const int64_t* numels, cc_yolo** out);
+/* Same with options.  CC_YOLO_FP32_ACCURATE: the fp32-accurate mode — activations stored in fp32, every conv as six
+ * bf16 plane products of a 3-way split of both operands on the same tcgen05 kernel (fp32 accumulation), exact SiLU.  The
+ * reference computes in fp32 end to end; this is the mode whose boxes / scores are compared with the fp32
+ * oracle at the north-star tolerance.  Costs ~6x the tensor work and 2x the activation bytes of the default (bf16) mode. */
+#define CC_YOLO_FP32_ACCURATE 1
+int cc_yolo_create_ex(const char* size, int flags, int n_tensors, const char* const* names, const float* const* h_data,
+                      const int64_t* numels, cc_yolo** out);
 int cc_yolo_destroy(cc_yolo* h);
 
 /* YOLOv9.__call__ (detection/yolov9.py:375-388) for a batch of same-shape frames.
@@ -74,11 +81,28 @@ int cc_yolo_forward(cc_yolo* h, const void* d_frames, int is_f32, int B, int Hf,
 int cc_yolo_plan_info(cc_yolo* h, int is_f32, int B, int Hf, int Wf, int res, int* net_h, int* net_w, int* anchors,
                       int* launches, double* conv_flops, double* act_bytes);
 
+/* Workspace.  Every cached plan of a handle carves its activations out of ONE device workspace (size of the largest plan;
+ * at most 16 plans are kept, least recently used goes first), so a process that sees many batch sizes / frame shapes does
+ * not accumulate buffers.  By default the library owns it and grows it on demand (a growth frees and reallocates: it
+ * synchronises the device once, and the plans of the old workspace are rebuilt on their next use).  A caller that wants no
+ * allocation after start-up sizes it with cc_yolo_workspace_bytes for its largest shape and hands it over with
+ * cc_yolo_set_workspace (256-byte aligned device memory, owned by the caller; d_workspace = NULL returns to the
+ * library-owned one); a plan that does not fit a caller-owned workspace fails with CC_ERR_INVALID.  The plans of one
+ * handle share the memory: run them in stream order (one stream per handle). */
+int cc_yolo_workspace_bytes(cc_yolo* h, int is_f32, int B, int Hf, int Wf, int res, size_t* bytes);
+int cc_yolo_set_workspace(cc_yolo* h, void* d_workspace, size_t bytes);
+
 /* measurement: per-op device time of one forward (CUDA events between launches on `stream`; synchronises).
  * Up to `cap` entries of ms / algorithmic conv FLOPs / algorithmic HBM bytes / kernel kind / op name (pointers valid
  * while h lives). */
 int cc_yolo_profile(cc_yolo* h, const void* d_frames, int is_f32, int B, int Hf, int Wf, int res, float* d_out, int cap,
                     float* ms, double* flops, double* bytes, const char** kinds, const char** names, int* n_ops, void* stream);
+
+/* measurement: in-situ device timeline of one forward, no events between the launches (so programmatic dependent launch
+ * overlaps exactly as in production).  For op i, host_ns[3i..3i+2] = globaltimer ns of (first CTA entered, grid
+ * dependency released, last CTA exited) for the tensor-core conv launches, zeros for the other kernels.  Synchronises. */
+int cc_yolo_trace(cc_yolo* h, const void* d_frames, int is_f32, int B, int Hf, int Wf, int res, float* d_out, int cap,
+                  unsigned long long* host_ns, const char** kinds, const char** names, double* flops, int* n_ops, void* stream);
 
 /* parity tap: after a forward, copy the output of graph layer `layer` (index into the reference's self.model list,
  * detection/yolov9.py:303-371) to dense fp32 [B,H,W,C].  d_dst == NULL only queries C/H/W (C = 0: no tensor). */
@@ -122,11 +146,22 @@ int cc_clip_destroy(cc_clip* h);
 int cc_clip_encode_image(cc_clip* h, const float* d_x, int B, float* d_out, long long out_row_stride, void* stream);
 /* encode_text (models/objects.py:145-186), batched: d_ids [B,ctx] int32 ([49406]+BPE+[49407], zero padded). */
 int cc_clip_encode_text(cc_clip* h, const int32_t* d_ids, int B, float* d_out, long long out_row_stride, void* stream);
+/* Workspace of the CLIP plans, same contract as cc_yolo_workspace_bytes / cc_yolo_set_workspace (text != 0: text tower). */
+int cc_clip_workspace_bytes(cc_clip* h, int text, int B, size_t* bytes);
+int cc_clip_set_workspace(cc_clip* h, void* d_workspace, size_t bytes);
 /* per-op device timing of one encode (text != 0: text tower). */
 int cc_clip_profile(cc_clip* h, int text, const void* d_in, int B, float* d_out, int cap, float* ms, double* flops,
                     const char** names, int* n_ops, double* total_flops, void* stream);
 /* ObjectFinder.search inner loop (models/objects.py:365-376): d_scores[q*N + n] = <d_index[n,:], d_q[q,:]>, fp32. */
 int cc_search_scores(const float* d_index, int N, int D, const float* d_q, int Q, float* d_scores, void* stream);
+
+/* ObjectFinder.search with the selection on the device (models/objects.py:365-390): every index row n belongs to group
+ * d_group[n] in [0, G) — the rows of one object id share a group, a row without an object id has its own — and rows with
+ * d_mask[n] == 0 are skipped (camera / date filter; NULL = no filter).  Per group the best-scoring row is kept, and the k
+ * best groups are written in descending score order to d_rows[k] (index row, -1 past the last match) / d_scores[k]; an
+ * exact tie goes to the lower row.  d_workspace: 8 * max(G,1) bytes of device scratch.  Only the k winners cross PCIe. */
+int cc_search_topk(const float* d_index, int N, int D, const float* d_q, const int32_t* d_group, const uint8_t* d_mask, int G, int k,
+                   void* d_workspace, int32_t* d_rows, float* d_scores, void* stream);
 
 /* Crop + ObjectFinder.preprocess on the device, for objects cut out of frames already resident for the detector:
  * frame[y1:y2, x1:x2] (clearcam.py:396) -> BGR->RGB when bgr != 0 (models/objects.py:249) -> cv2.resize((size,size),

@@ -44,7 +44,8 @@ def test_step_routes_results_to_cameras_and_tracks():
     cb.add_camera("cam2", classes={0})                      # class filter drops class 2
     for t in range(4):
         res = cb.step(_frames(t))
-    assert sorted(det.calls[-3:]) == [(1, 36, 96, 3), (1, 48, 64, 3), (3, 48, 64, 3)]      # one call per shape group
+    # one call per shape group; the 3-camera group is padded to the batch bucket 4 (zero frame, result dropped)
+    assert sorted(det.calls[-3:]) == [(1, 36, 96, 3), (1, 48, 64, 3), (4, 48, 64, 3)]
     assert set(res) == {"cam0", "cam1", "cam2", "wide", "float"}
     for name, base in [("cam0", 0), ("wide", 100), ("float", 70)]:
         r = res[name]
@@ -58,6 +59,27 @@ def test_step_routes_results_to_cameras_and_tracks():
         rows = det.detect_batch(torch.from_numpy(_frames(t)["cam0"])[None])[0].numpy()
         exp = solo.update(rows, 0.5)
     np.testing.assert_array_equal(exp[0].tlwh, res["cam0"].targets[0].tlwh)
+
+
+def test_varying_camera_count_uses_a_bounded_set_of_batch_sizes():
+    """The number of cameras with a new frame changes every step; the detector must only ever see bucket sizes (each
+    distinct batch size is a cached plan in the library)."""
+    from clearcam_b200.utils.helpers import batch_bucket
+    assert [batch_bucket(n) for n in (1, 2, 3, 5, 9, 13, 17, 25, 33, 100)] == [1, 2, 4, 8, 12, 16, 24, 32, 48, 112]
+    assert all(batch_bucket(n) >= n and batch_bucket(n) <= max(4 * n // 3 + 1, n + 15) for n in range(1, 300))
+    det = FakeDetector()
+    cb = CameraBatch(det)
+    rng = np.random.default_rng(0)
+    for t in range(40):
+        k = int(rng.integers(1, 40))
+        res = cb.step({f"c{i}": np.full((16, 16, 3), (i + t) % 200, np.uint8) for i in range(k)})
+        assert len(res) == k and all(abs(res[f"c{i}"].rows[0, 0] - (i + t) % 200) < 1e-4 for i in range(k))
+    assert {c[0] for c in det.calls} <= {1, 2, 4, 8, 12, 16, 24, 32, 48}
+    assert len(cb._stage) <= 9
+    # a removed and re-added camera (fresh mailbox, frame_num restarts) is not mistaken for "already seen"
+    cb._seen["c0"] = 0
+    cb.remove_camera("c0")
+    assert "c0" not in cb._seen
 
 
 def test_jit_infer_is_a_plain_call_keyed_by_shape():

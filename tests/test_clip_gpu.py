@@ -84,6 +84,70 @@ def test_search_matches_reference_semantics(tmp_path):
     assert all("/cameras/cam1/" in p for p, _ in f.search(top_k=50, text_embedding=q[0].numpy(), cam_name="cam1"))
 
 
+def _reference_search(emb, qv, top_k, cam_name=None, timestamp=None):
+    """models/objects.py:356-390 restated on the host (scores by the oracle's plain dot product)."""
+    import os
+    from clearcam_b200.models.objects import event_img_info
+    sims = []
+    for path, e in emb.items():
+        if e is None:
+            continue
+        similarity = float(oc.search_scores(torch.from_numpy(np.asarray(e, np.float32).reshape(1, -1)), torch.from_numpy(qv))[0])
+        norm = path.replace("\\", "/")
+        if cam_name and f"/cameras/{cam_name}/" not in norm:
+            continue
+        if timestamp and f"/objects/{timestamp}/" not in norm and "/objects/video/" not in norm:
+            continue
+        filename = os.path.basename(path)
+        if filename.lower().endswith(".jpg"):
+            oid = event_img_info(filename.split(".jpg")[0])["object_id"] if "_" in filename else None
+            sims.append((path, similarity, oid))
+    if any(s_[2] for s_ in sims):
+        best = {}
+        for path, score, oid in sims:
+            if oid is not None and (oid not in best or score > best[oid][1]):
+                best[oid] = (path, score)
+        results = list(best.values()) + [(p_, s_) for p_, s_, oid in sims if oid is None]
+    else:
+        results = [(p_, s_) for p_, s_, _ in sims]
+    results.sort(key=lambda x: x[1], reverse=True)
+    return results[:top_k]
+
+
+def test_device_topk_search_equals_the_reference_loop(tmp_path):
+    """cc_search_topk (scores + best-per-object-id + top-k on the device) against the reference's Python loop on an index
+    with every kind of row: several cameras and dates, the shared 'video' folder, rows without an object id, non-jpg rows,
+    a replaced embedding, and more requested results than matches."""
+    g = torch.Generator().manual_seed(3)
+    N, D = 700, 512
+    index = torch.nn.functional.normalize(torch.randn(N, D, generator=g), dim=-1).numpy()
+    qs = torch.nn.functional.normalize(torch.randn(4, D, generator=g), dim=-1).numpy()
+    emb = {}
+    for i in range(N):
+        cam, date = f"cam{i % 3}", ("video" if i % 11 == 0 else f"2026-01-0{1 + i % 4}")
+        name = f"{1000 + i}_{i % 57}_{i % 5}.jpg" if i % 7 else (f"snap{i}.jpg" if i % 2 else f"{1000 + i}_{i % 57}_0.png")
+        emb[f"/data/cameras/{cam}/objects/{date}/{name}"] = index[i:i + 1]
+    emb["/data/cameras/cam0/objects/2026-01-01/none.jpg"] = None
+    f = ObjectFinder(base_path=str(tmp_path))
+    f.image_embeddings = emb
+    cases = [dict(top_k=10), dict(top_k=25, cam_name="cam1"), dict(top_k=10, timestamp="2026-01-02"),
+             dict(top_k=400, cam_name="cam2", timestamp="2026-01-03"), dict(top_k=5, cam_name="nope"), dict(top_k=1000)]
+    for qv in qs[:2]:
+        for kw in cases:
+            got, want = f.search(text_embedding=qv, **kw), _reference_search(emb, qv, **kw)
+            assert [p_ for p_, _ in got] == [p_ for p_, _ in want], kw
+            assert np.allclose([s_ for _, s_ in got], [s_ for _, s_ in want], atol=1e-5)
+    # no row with an object id among the candidates -> every row stands for itself (:377)
+    f2 = ObjectFinder(base_path=str(tmp_path))
+    f2.image_embeddings = {f"/data/cameras/cam0/objects/video/frame{i}.jpg": index[i:i + 1] for i in range(50)}
+    got, want = f2.search(text_embedding=qs[2], top_k=20), _reference_search(f2.image_embeddings, qs[2], 20)
+    assert [p_ for p_, _ in got] == [p_ for p_, _ in want]
+    # an embedding replaced under an existing path is picked up (the device index is fingerprinted by value identity)
+    key = next(iter(f2.image_embeddings))
+    f2.image_embeddings[key] = qs[3:4].copy()
+    assert f2.search(text_embedding=qs[3], top_k=1)[0][0] == key
+
+
 # ------------------------------------------------------------------------------------------------ crop -> CLIP input
 def test_device_crop_preprocess_bit_exact():
     """cc_clip_preprocess == crop + cvtColor + ObjectFinder.preprocess with OpenCV's bicubic (oracle pinned to cv2)."""

@@ -96,3 +96,35 @@ def test_camera_batch_takes_unseen_frames_from_mailboxes():
     res = cb.step_mailboxes(boxes)
     assert set(res) == {"a", "b"} and res["a"].rows[0, 0] == 6 and res["b"].rows[0, 0] == 9
     assert len(res["a"].targets) == 1 and res["a"].targets[0].tracklet_len >= 1
+
+
+def test_reader_survives_a_camera_that_is_down_and_stop_unblocks_a_silent_one():
+    """open_stream() raising (ffmpeg / camera down) must not kill the reader thread: it retries with back-off and counts
+    the failures; stop() closes the stream so a read blocked on a silent camera returns (the reference's frame_loop keeps
+    retrying, clearcam.py:401-421)."""
+    attempts = []
+    r_fd, w_fd = os.pipe()                                  # a camera that connects but never sends a byte
+
+    def open_stream():
+        attempts.append(time.time())
+        if len(attempts) <= 3:
+            raise OSError("camera unreachable")
+        return os.fdopen(r_fd, "rb", buffering=0)
+
+    mb = FrameMailbox(H, W, pin=False)
+    rd = PipeReader(mb, open_stream, max_fail=2, retry_sleep=0.01)
+    rd.start()
+    t0 = time.time()
+    while time.time() - t0 < 5 and len(attempts) < 4:
+        time.sleep(0.005)
+    assert rd.is_alive() and rd.open_errors == 3 and isinstance(rd.last_error, OSError)
+    time.sleep(0.05)                                        # now blocked in readinto() on the silent pipe
+    os.write(w_fd, _frame(7).tobytes())
+    t0 = time.time()
+    while time.time() - t0 < 5 and mb.latest(-1) is None:
+        time.sleep(0.005)
+    assert mb.latest(-1) is not None                        # the stream opened on the 4th attempt delivers
+    rd.stop()
+    os.close(w_fd)
+    rd.join(timeout=5)
+    assert not rd.is_alive()

@@ -43,7 +43,7 @@ def main():
                 shape, rest = line.split(":", 1)
                 row[shape.strip()] = rest.split("ms")[0].strip() + " ms"
         if bench:
-            cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--no-cpu"] + (["--batch", batch] if batch else [])
+            cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--no-cpu", "--no-clip"] + (["--batch", batch] if batch else [])
             out = subprocess.run(cmd, env=env, capture_output=True, text=True).stdout.strip().splitlines()
             try:
                 d = json.loads(out[-1])
