@@ -1,7 +1,12 @@
 // Multi-head attention on tcgen05 (sm_100a), d_head = 64:  ctx = softmax(Q K^T / 8 [+ causal mask]) V per (image, head).
 // Reference: models/objects.py:108-118 (image tower), :157-168 (text tower, causal).
 //
-// One CTA per (image, head); K and V^T of the head are TMA-loaded once, then the CTA walks the 128-query blocks:
+// One CTA per (group of G consecutive images, head): the tokens of the G images are one packed sequence of G*L rows (they are
+// consecutive rows of the QKV buffer) with a block-diagonal mask — a query row attends the keys of its own image only.  Short
+// sequences (ViT-B/32: 50 tokens, text: 77) fill the 128-row MMA blocks this way (G = 5 -> 250 of 256 rows, G = 3 -> 231 of
+// 256) and share one TMEM allocation / barrier set-up / K,V load per CTA; the long one (ViT-L/14: 257) runs with G = 1.
+// Softmax work is NOT wasted on the mask: a row reads and exponentiates only its own image's key columns.
+// K and V^T of the group are TMA-loaded once, then the CTA walks the 128-query blocks:
 //   S[128 x Lk]  = Q[128 x 64] . K[Lk x 64]^T      tcgen05.mma, accumulators in TMEM columns [0, Lk)
 //   softmax      : 4 warps, thread == query row, two passes over TMEM (row max, then exp2/sum); P (bf16, unnormalised,
 //                  <= 1) is written straight into the 128B-swizzled K-major layout the second MMA reads as its A operand
@@ -16,23 +21,27 @@
 
 namespace cc {
 
-static constexpr int kMaxLk = 448;   // S uses TMEM columns [0, Lk), O the 64 columns after it: Lk + 64 <= 512
+static constexpr int kMaxLk = 384;   // S uses TMEM columns [0, Lk), O the 64 columns after it (Lk + 64 <= 512); shared memory holds K, V^T, P for 384 keys
 
 struct AttnParams {
   CUtensorMap tmQK;   // qkv viewed as [B*L rows][3W cols], box 64 rows x 64 cols
   CUtensorMap tmVt;   // Vt [B*H*64 rows][Lk cols], box 64 rows x 64 cols
   __nv_bfloat16* ctx;
   int B, L, Lk, H, W, causal;
+  int G;           // images per CTA (packed sequence of G*L tokens, Lk = ceil(G*L / 64) * 64 key columns)
   int tmem_cols;   // power of two >= Lk + 64
 };
 
 // ---------------------------------------------------------------- V^T pre-pass
-__global__ void __launch_bounds__(256) vt_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ vt, int L,
-                                                 int Lk, int H, int W) {
+// (L here = tokens of one group = G * tokens per image; the last group of a batch may hold fewer: Ltot bounds the rows)
+__global__ void __launch_bounds__(256) vt_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ vt, int Lg,
+                                                 long long Ltot, int Lk, int H, int W) {
   __shared__ __nv_bfloat16 tile[64][66];
   const int bh = blockIdx.x, b = bh / H, h = bh % H;
   const int t0 = blockIdx.y * 64;
-  const __nv_bfloat16* src = qkv + static_cast<long long>(b) * L * 3 * W + 2 * W + h * 64;
+  const long long rem = Ltot - static_cast<long long>(b) * Lg;
+  const int L = rem < Lg ? static_cast<int>(rem) : Lg;
+  const __nv_bfloat16* src = qkv + static_cast<long long>(b) * Lg * 3 * W + 2 * W + h * 64;
   for (int i = threadIdx.x; i < 64 * 8; i += 256) {   // 64 tokens x 8 chunks of 8 d
     const int t = i >> 3, c = (i & 7) * 8;
     uint4 v = make_uint4(0, 0, 0, 0);
@@ -69,8 +78,10 @@ __global__ void __launch_bounds__(160) attention_tc_kernel(const __grid_constant
   uint64_t* bar_oe = bars + 6;   // O read back (4 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
 
-  const int bh = blockIdx.x, b = bh / p.H, h = bh % p.H;
-  const int nqb = (p.L + 127) >> 7;
+  const int bh = blockIdx.x, grp = bh / p.H, h = bh % p.H;
+  const int nimg = (p.B - grp * p.G) < p.G ? (p.B - grp * p.G) : p.G;   // images in this group (the last one may be short)
+  const int Lt = nimg * p.L;                      // tokens of the packed sequence
+  const int nqb = (Lt + 127) >> 7;
   const uint32_t kOCol = p.Lk;                    // O accumulator right after S
 
   if (warp == 0) {
@@ -92,7 +103,7 @@ __global__ void __launch_bounds__(160) attention_tc_kernel(const __grid_constant
 
   if (warp == 0) {
     // ===================== control warp: TMA loads + MMA issue (one elected lane) =====================
-    const int row0 = b * p.L;
+    const int row0 = grp * p.G * p.L;
     if (lane == 0) {
       mbar_arrive_expect_tx(bar_k, p.Lk * 128);
       for (int j = 0; j < nkb; ++j) tma_load_2d(sK + j * 8192, &p.tmQK, bar_k, p.W + h * 64, row0 + 64 * j);
@@ -160,22 +171,36 @@ __global__ void __launch_bounds__(160) attention_tc_kernel(const __grid_constant
     const float kScale = 0.125f * 1.4426950408889634f;   // 1/sqrt(64) * log2(e)
     for (int qb = 0; qb < nqb; ++qb) {
       const uint32_t ph = qb & 1;
-      const int qi = qb * 128 + row;              // query index inside the sequence
-      const int lim = p.causal ? (qi < p.L - 1 ? qi : p.L - 1) : p.L - 1;   // last visible key
+      const int qi = qb * 128 + row;              // query index inside the packed sequence
+      // keys this row may see: those of its own image, up to itself when causal
+      int lo = 0, lim = 0;
+      if (qi < Lt) {
+        const int img = qi / p.L;
+        lo = img * p.L;
+        lim = p.causal ? qi : lo + p.L - 1;
+      }
+      const int c_lo = lo & ~15;                  // 16-column chunks that intersect [lo, lim]
       mbar_wait(bar_s, ph);
       tc_fence_after();
       float m = -INFINITY;
-      for (int c0 = 0; c0 < p.Lk; c0 += 16) {
+      for (int c0 = c_lo; c0 <= lim; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(t_row + c0, v);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          if (c0 + j <= lim) m = fmaxf(m, __uint_as_float(v[j]));
+          if (c0 + j >= lo && c0 + j <= lim) m = fmaxf(m, __uint_as_float(v[j]));
       }
       const float mc = m * kScale;
       float sum = 0.f;
       for (int c0 = 0; c0 < p.Lk; c0 += 16) {
+        uint8_t* blk = sP + (c0 >> 6) * 16384 + row * 128;
+        const uint32_t i0 = (c0 & 63) >> 3;
+        if (c0 < c_lo || c0 > lim) {             // another image's keys: P = 0, no TMEM read, no exponentials
+          *reinterpret_cast<uint4*>(blk + ((i0 ^ (row & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(blk + (((i0 + 1) ^ (row & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+          continue;
+        }
         uint32_t v[16];
         tmem_ld16(t_row + c0, v);
         tmem_ld_wait();
@@ -184,11 +209,9 @@ __global__ void __launch_bounds__(160) attention_tc_kernel(const __grid_constant
         for (int j = 0; j < 16; ++j) {
           float x;
           asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(x) : "f"(fmaf(__uint_as_float(v[j]), kScale, -mc)));
-          e[j] = (c0 + j <= lim) ? x : 0.f;
+          e[j] = (c0 + j >= lo && c0 + j <= lim) ? x : 0.f;
           sum += e[j];
         }
-        uint8_t* blk = sP + (c0 >> 6) * 16384 + row * 128;
-        const uint32_t i0 = (c0 & 63) >> 3;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           uint32_t w[4];
@@ -208,13 +231,13 @@ __global__ void __launch_bounds__(160) attention_tc_kernel(const __grid_constant
       mbar_wait(bar_o, ph);
       tc_fence_after();
       const float inv = 1.0f / sum;
-      __nv_bfloat16* out = p.ctx + (static_cast<long long>(b) * p.L + qi) * p.W + h * 64;
+      __nv_bfloat16* out = p.ctx + (static_cast<long long>(grp) * p.G * p.L + qi) * p.W + h * 64;
 #pragma unroll
       for (int c0 = 0; c0 < 64; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(t_row + kOCol + c0, v);
         tmem_ld_wait();
-        if (qi < p.L) {
+        if (qi < Lt) {
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
             uint32_t w[4];
@@ -242,30 +265,46 @@ __global__ void __launch_bounds__(160) attention_tc_kernel(const __grid_constant
 }
 
 // ---------------------------------------------------------------- host
+// images per CTA: the packing that fills the 128-row query blocks best while the packed key range stays within 256 columns
+// (larger G only adds masked S / PV columns); one image per CTA when a single image already spans more than 256 keys
+static int attention_group(int B, int L) {
+  int best = 1;
+  double best_u = -1;
+  for (int g = 1; g <= B && g <= 16; ++g) {
+    const int rows = g * L, lk = (rows + 63) / 64 * 64;
+    if (g > 1 && lk > 256) break;
+    const double u = double(rows) / (128.0 * ((rows + 127) / 128));
+    if (u > best_u + 1e-9 || (u > best_u - 1e-9 && g > best)) { best_u = u; best = g; }
+  }
+  return best;
+}
+static int attention_lk(int B, int L) { return (attention_group(B, L) * L + 63) / 64 * 64; }
+
 bool attention_tc_supported(int L) {
-  // CC_ATTN_TC: 0 = never, 1 (default) = where it wins on B200 (more than one 128-query block: ViT-L/14's 257 tokens;
-  // the 50- and 77-token sequences stay on the mma.sync kernel, measured 25 % faster there), 2 = wherever it fits.
-  // Read when a plan is built, so tests can force either path.
+  // CC_ATTN_TC: 0 = never (legacy mma.sync kernel), 1 (default) / 2 = wherever it fits.  Read when a plan is built, so tests
+  // can force either path.  (Round 1 kept the 50- and 77-token sequences on mma.sync: one (image, head) per CTA left most of
+  // the 128-row block empty; packed groups removed that.)
   const char* e = getenv("CC_ATTN_TC");
   const int mode = e ? atoi(e) : 1;
   const int Lk = (L + 63) / 64 * 64;
   if (mode == 0 || Lk > kMaxLk) return false;
-  return mode >= 2 || L > 128;
+  return true;
 }
 size_t attention_tc_workspace_bytes(int B, int L, int H) {
-  const int Lk = (L + 63) / 64 * 64;
-  return static_cast<size_t>(B) * H * 64 * Lk * 2;
+  const int G = attention_group(B, L);
+  return static_cast<size_t>((B + G - 1) / G) * H * 64 * attention_lk(B, L) * 2;
 }
 
 int attention_tc_launch(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, __nv_bfloat16* vt_ws, int B, int L, int H, int causal,
                         cudaStream_t st) {
   if (B == 0) return CC_OK;
-  const int W = H * 64, Lk = (L + 63) / 64 * 64, nkb = Lk / 64;
+  const int G = attention_group(B, L), NG = (B + G - 1) / G;
+  const int W = H * 64, Lk = attention_lk(B, L), nkb = Lk / 64;
   CC_REQUIRE(Lk <= kMaxLk, "attention_tc: sequence length %d too long", L);
   PFN_encodeTiled enc = get_encode_tiled();
   CC_REQUIRE(enc != nullptr, "attention_tc: cuTensorMapEncodeTiled unavailable");
   AttnParams p{};
-  p.ctx = ctx; p.B = B; p.L = L; p.Lk = Lk; p.H = H; p.W = W; p.causal = causal;
+  p.ctx = ctx; p.B = B; p.L = L; p.Lk = Lk; p.H = H; p.W = W; p.causal = causal; p.G = G;
   p.tmem_cols = 32;
   while (p.tmem_cols < Lk + 64) p.tmem_cols <<= 1;
   {
@@ -278,7 +317,7 @@ int attention_tc_launch(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, __nv_bfloa
     CC_REQUIRE(r == CUDA_SUCCESS, "attention_tc: tensor map (QK) failed: %d", int(r));
   }
   {
-    cuuint64_t dims[2] = {cuuint64_t(Lk), cuuint64_t(B) * H * 64};
+    cuuint64_t dims[2] = {cuuint64_t(Lk), cuuint64_t(NG) * H * 64};
     cuuint64_t strides[1] = {cuuint64_t(Lk) * 2};
     cuuint32_t box[2] = {64, 64}, estr[2] = {1, 1};
     CUresult r = enc(&p.tmVt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, vt_ws, dims, strides, box, estr,
@@ -286,7 +325,7 @@ int attention_tc_launch(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, __nv_bfloa
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     CC_REQUIRE(r == CUDA_SUCCESS, "attention_tc: tensor map (Vt) failed: %d", int(r));
   }
-  vt_kernel<<<dim3(B * H, nkb), 256, 0, st>>>(qkv, vt_ws, L, Lk, H, W);
+  vt_kernel<<<dim3(NG * H, nkb), 256, 0, st>>>(qkv, vt_ws, G * L, static_cast<long long>(B) * L, Lk, H, W);
   CC_CHECK_CUDA(cudaGetLastError());
   const int smem = 1024 + 128 * 128 + Lk * 128 + nkb * 8192 + nkb * 16384 + 128;
   static bool attr_set = false;
@@ -294,7 +333,7 @@ int attention_tc_launch(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, __nv_bfloa
     CC_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  attention_tc_kernel<<<B * H, 160, smem, st>>>(p);
+  attention_tc_kernel<<<NG * H, 160, smem, st>>>(p);
   CC_CHECK_CUDA(cudaGetLastError());
   return CC_OK;
 }

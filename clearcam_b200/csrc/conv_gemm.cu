@@ -79,6 +79,22 @@ __device__ __forceinline__ TileXY tile_origin(const GemmParams& p, int tile, int
   return t;
 }
 
+// Static tile schedule.  A CTA walks "slots" first, first+step, ... < limit; a slot is a tile, or — with CTA pairs — a super
+// tile (two adjacent M tiles x one N block) of which the CTA takes the M tile of its cluster rank.  An odd M-tile count leaves
+// the last pair's second CTA a tile past the end: it runs the same protocol on zero-filled loads and fully clipped stores.
+struct Sched { int first, step, limit, rank; };
+__device__ __forceinline__ Sched make_sched(const GemmParams& p) {
+  Sched s;
+  if (p.pair) { s.first = blockIdx.x >> 1; s.step = gridDim.x >> 1; s.limit = p.n_super; s.rank = static_cast<int>(cluster_ctarank()); }
+  else { s.first = blockIdx.x; s.step = gridDim.x; s.limit = p.num_tiles; s.rank = 0; }
+  return s;
+}
+__device__ __forceinline__ int slot_tile(const GemmParams& p, const Sched& s, int slot) {
+  if (!p.pair) return slot;
+  const int mp = fdiv(slot, p.fd_nb);
+  return (2 * mp + s.rank) * p.n_blocks + (slot - mp * p.n_blocks);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -112,7 +128,9 @@ __device__ __forceinline__ void mma_issuer(const GemmParams& p, uint8_t* sA, uin
     const uint64_t d_halo = dconst | (static_cast<uint64_t>((16u * row_bytes) >> 4) << 32);   // halo views: 16-px row pitch
     const uint32_t sA16 = (smem_u32(sA) & 0x3FFFF) >> 4, sB16 = (smem_u32(sB) & 0x3FFFF) >> 4;
     const uint32_t a16 = a_bytes >> 4, b16 = b_bytes >> 4, h16 = p.halo_bytes >> 4;
-    const int num_tiles = p.num_tiles, tstride = gridDim.x, cpt = p.chunks_per_tap, hstages = p.halo_stages;
+    const Sched sc = make_sched(p);
+    const int cpt = p.chunks_per_tap, hstages = p.halo_stages;
+    const bool pair = p.pair != 0;
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -126,7 +144,7 @@ __device__ __forceinline__ void mma_issuer(const GemmParams& p, uint8_t* sA, uin
       const uint32_t rstep16 = ((16u << p.lTN) * row_bytes) >> 4;  // one halo row block (TN images x 16 px), in 16-B units
       const uint32_t sstep16 = row_bytes >> 4;                      // one pixel
       const uint32_t btap16 = cpt * b16;                            // resident weights: descriptor step between taps
-      for (int tile = blockIdx.x; tile < num_tiles; tile += tstride) {
+      for (int slot = sc.first; slot < sc.limit; slot += sc.step) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * acc_cols;
@@ -154,7 +172,7 @@ __device__ __forceinline__ void mma_issuer(const GemmParams& p, uint8_t* sA, uin
                 const int r = t / 3;
                 mma_kblock<KPB>(d_tmem, a_base + (r * rstep16 + (t - 3 * r) * sstep16), d_tile | (sB16 + stage * b16), idesc,
                                 static_cast<uint32_t>((ch | t) != 0));
-                umma_commit(&empty_bar[stage]);
+                if (pair) umma_commit_mc(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
                 if (t == 8) {
                   umma_commit(&aempty_bar[sa]);
                   if (ch == cpt - 1) umma_commit(&tfull_bar[acc]);
@@ -170,7 +188,7 @@ __device__ __forceinline__ void mma_issuer(const GemmParams& p, uint8_t* sA, uin
       }
     } else {
       const bool whole_tile = BRES && num_kb <= 4 && num_kb <= S && !(p.dbg & 8);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += tstride) {
+      for (int slot = sc.first; slot < sc.limit; slot += sc.step) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * acc_cols;
@@ -206,7 +224,8 @@ __device__ __forceinline__ void mma_issuer(const GemmParams& p, uint8_t* sA, uin
             if (elect_one()) {
               mma_kblock<KPB>(d_tmem, d_tile | (sA16 + stage * a16), d_tile | (sB16 + (BRES ? kb : stage) * b16), idesc,
                               static_cast<uint32_t>(kb != 0));
-              umma_commit(&empty_bar[stage]);                         // frees this smem stage once the MMAs have read it
+              // frees this smem stage once the MMAs have read it (in both CTAs of a pair: the peer multicasts into it)
+              if (pair) umma_commit_mc(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
               if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);     // accumulator complete -> epilogue
             }
             __syncwarp();
@@ -265,7 +284,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < S; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], p.pair ? 2 : 1);   // pairs: the MMA warps of both CTAs release a stage
     }
     for (int i = 0; i < kMaxAcc; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -286,8 +305,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   }
   tc_fence_before();
   __syncthreads();
+  if (p.pair) cluster_sync_all();   // the peer's barriers must exist before anything is multicast into its shared memory
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const Sched sc = make_sched(p);
   // PDL: let the next kernel start its prologue as our CTAs retire; everything that only touches WEIGHTS (bias above,
   // resident / first weight tiles below) runs before griddepcontrol.wait, i.e. overlaps the previous kernel's tail.
   // Activations of the previous layer are read only by the TMA producer (A operand) and the epilogue (residual):
@@ -311,8 +332,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         int sa = 0;
         uint32_t pa = 0;
         const int cin = p.chunks_per_tap * p.BK;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-          const TileXY tx = tile_origin(p, tile, 3);
+        const uint32_t hb = b_bytes >> 1;
+        for (int slot = sc.first; slot < sc.limit; slot += sc.step) {
+          const TileXY tx = tile_origin(p, slot_tile(p, sc, slot), 3);
           const int nb = tx.nb, w0 = tx.w0, h0 = tx.h0, n0 = tx.n0;
           for (int ch = 0; ch < p.chunks_per_tap; ++ch) {
             mbar_wait(&aempty_bar[sa], pa ^ 1);
@@ -326,14 +348,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
               for (int t = 0; t < 9; ++t) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 mbar_arrive_expect_tx(&full_bar[stage], b_bytes);
-                tma_load_2d(sB + stage * b_bytes, &p.tmB, &full_bar[stage], t * cin + ch * p.BK, nb * p.BN);
+                if (p.pair)   // my half of the weight tile, to both CTAs; the peer sends the other half
+                  tma_load_2d_mc(sB + stage * b_bytes + sc.rank * hb, &p.tmB, &full_bar[stage], t * cin + ch * p.BK,
+                                 nb * p.BN + sc.rank * (p.BN >> 1), 3);
+                else tma_load_2d(sB + stage * b_bytes, &p.tmB, &full_bar[stage], t * cin + ch * p.BK, nb * p.BN);
                 if (++stage == S) { stage = 0; phase ^= 1; }
               }
           }
         }
       } else
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const TileXY tx = tile_origin(p, tile, p.lTW);
+      for (int slot = sc.first; slot < sc.limit; slot += sc.step) {
+        const TileXY tx = tile_origin(p, slot_tile(p, sc, slot), p.lTW);
         const int nb = tx.nb, w0 = tx.w0, h0 = tx.h0, n0 = tx.n0;
         int kb = 0;
         for (int t = 0; t < p.num_taps; ++t) {
@@ -347,7 +372,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             mbar_arrive_expect_tx(&full_bar[stage], (p.dbg & 4) ? (p.b_res ? 0 : b_bytes) : (p.b_res ? a_bytes : a_bytes + b_bytes));
             if (!(p.dbg & 4))
               tma_load_5d(sA + stage * a_bytes, &p.tmA, &full_bar[stage], c_base + ch * p.BK, c1, c2, c3, c4);
-            if (!p.b_res) tma_load_2d(sB + stage * b_bytes, &p.tmB, &full_bar[stage], kb * p.BK, nb * p.BN);
+            if (p.pair)
+              tma_load_2d_mc(sB + stage * b_bytes + sc.rank * (b_bytes >> 1), &p.tmB, &full_bar[stage], kb * p.BK,
+                             nb * p.BN + sc.rank * (p.BN >> 1), 3);
+            else if (!p.b_res) tma_load_2d(sB + stage * b_bytes, &p.tmB, &full_bar[stage], kb * p.BK, nb * p.BN);
             if (++stage == S) { stage = 0; phase ^= 1; }
           }
         }
@@ -397,8 +425,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     // previous store has read the buffer
     auto issue_res = [&](uint32_t k) {
       const int jg = static_cast<int>(k) / passes_per_tile;                          // k-th pass of this group
-      const int tile_k = blockIdx.x + (grp + jg * NG) * gridDim.x;
-      if (tile_k >= p.num_tiles) return;
+      const int slot_k = sc.first + (grp + jg * NG) * sc.step;
+      if (slot_k >= sc.limit) return;
+      const int tile_k = slot_tile(p, sc, slot_k);
       const int cc0k = (static_cast<int>(k) - jg * passes_per_tile) * CH;
       const int chnk = (p.BN - cc0k) < CH ? (p.BN - cc0k) : CH;
       const TileXY tk = tile_origin(p, tile_k, p.lTW);
@@ -413,8 +442,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     };
     pdl_wait();   // residual reads below depend on the previous kernel's output
     if (p.res_tma == 1 && gt == 0) issue_res(0);
-    for (int tile = blockIdx.x + grp * gridDim.x; tile < p.num_tiles; tile += NG * gridDim.x, ++tcount) {
-      const TileXY tx = tile_origin(p, tile, p.lTW);
+    for (int slot = sc.first + grp * sc.step; slot < sc.limit; slot += NG * sc.step, ++tcount) {
+      const TileXY tx = tile_origin(p, slot_tile(p, sc, slot), p.lTW);
       const int nb = tx.nb, w0 = tx.w0, h0 = tx.h0, n0 = tx.n0;
 
       // this thread's pixel (register phase: residual read)
@@ -593,6 +622,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 
   tc_fence_before();
   __syncthreads();
+  if (p.pair) cluster_sync_all();   // the peer may still multicast into / arrive on this CTA's shared memory until it is done too
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -753,17 +783,19 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
     CC_REQUIRE(r == CUDA_SUCCESS, "conv_gemm: cuTensorMapEncodeTiled(A) failed: %d (dims %llu,%llu,%llu,%llu,%llu)", int(r),
                dims[0], dims[1], dims[2], dims[3], dims[4]);
   }
-  {
+  auto encode_B = [&](int rows) -> int {     // weights [Cout][Ktot] bf16, box = BK x rows
     const cuuint64_t Ktot = cuuint64_t(d.k) * d.k * d.Cin;
     cuuint64_t dims[2] = {Ktot, cuuint64_t(d.Cout)};
     cuuint64_t strides[1] = {Ktot * 2};
-    cuuint32_t box[2] = {cuuint32_t(p.BK), cuuint32_t(BN)};
+    cuuint32_t box[2] = {cuuint32_t(p.BK), cuuint32_t(rows)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d.w), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     CC_REQUIRE(r == CUDA_SUCCESS, "conv_gemm: cuTensorMapEncodeTiled(B) failed: %d", int(r));
-  }
+    return CC_OK;
+  };
+  { int rcb = encode_B(BN); if (rcb) return rcb; }
 
   // ---- epilogue
   p.out = d.out; p.out_cs = d.out_cs; p.out_co = d.out_co; p.out_f32 = d.out_f32;
@@ -888,6 +920,19 @@ budget_again:
   }
   p.stages = S;
   L->grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  // CTA pairs: wide, streamed (non-resident) weight tiles are what the L2 -> SM fabric spends most of its bandwidth on
+  // (A 16 KB + B 32 KB per 128x256x64 block = 85 FLOP/B); two CTAs on adjacent M tiles of the same N block each load half of
+  // the weight tile and multicast it to both (16 + 16 KB = 128 FLOP/B)
+  static const int pair_env = getenv("CC_PAIR") ? atoi(getenv("CC_PAIR")) : 1;
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  p.pair = (pair_env && !p.b_res && BN >= 128 && (BN / 2) % 8 == 0 && m_tiles >= 2 && num_sms >= 2) ? 1 : 0;
+  p.n_super = ((m_tiles + 1) / 2) * p.n_blocks;
+  if (p.pair) {
+    int rcb = encode_B(BN / 2);
+    if (rcb) return rcb;
+    const int cap = num_sms & ~1;
+    L->grid = 2 * p.n_super < cap ? 2 * p.n_super : cap;
+  }
   L->flops = 2.0 * double(d.N) * Hout * Wout * d.Cout * d.k * d.k * d.Cin;
   L->bytes = double(d.N) * d.Hin * d.Win * d.Cin * 2 + double(d.N) * Hout * Wout * d.Cout * es * (d.res ? 2 : 1) +
              double(d.Cout) * d.k * d.k * d.Cin * 2;
@@ -906,11 +951,18 @@ static int launch_variant(const GemmLaunch& L, cudaStream_t stream) {
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = L.smem_bytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (L.p.pair) {
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
+  }
   CC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<ACT, F32>, L.p));
   return CC_OK;
 }

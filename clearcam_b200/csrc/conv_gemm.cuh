@@ -54,6 +54,9 @@ struct GemmParams {
   int32_t dbg;                        // CC_DBG bisection switches (never set in production): 1 no epilogue work, 4 no A loads
   int32_t n_acc;                      // TMEM accumulator slots == independent epilogue groups: 4 (BN <= 128) or 2
   int32_t lgw;                        // log2(warps per epilogue group): 2 or 3
+  // CTA pairs (2-CTA clusters): both CTAs of a pair work on the same N block of two adjacent M tiles, each TMA-loads half of
+  // every weight tile and multicasts it to both (halves the weight traffic L2 -> SM of the wide GEMMs, which are bound by it)
+  int32_t pair, n_super;              // enabled / number of (M-tile pair, N block) super tiles
   int32_t CH;                         // output columns per staging pass of one epilogue group
   unsigned long long* trace;          // optional device timeline slot [3]: first CTA entry, dependency released, last CTA exit (globaltimer ns)
 };

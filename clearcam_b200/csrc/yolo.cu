@@ -180,6 +180,13 @@ struct YoloPlan {
   double conv_flops = 0;
   int n_launch = 0;
   std::vector<T> layer_outs;   // per spec layer (parity taps)
+  // CUDA graph of the whole launch list (the analogue of the reference's TinyJit capture, utils/helpers.py:214-221).  Kernel
+  // arguments are baked into a graph, so it is captured once the caller has passed the same (frames, out, raw) pointers twice
+  // in a row — the steady state of a camera loop that reuses its buffers — and replayed while they stay the same.
+  cudaGraphExec_t gexec = nullptr;
+  const void* g_frames = nullptr; float* g_out = nullptr; float* g_raw = nullptr;      // pointers the graph was captured with
+  const void* l_frames = nullptr; float* l_out = nullptr; float* l_raw = nullptr;      // pointers of the previous call
+  ~YoloPlan() { if (gexec) cudaGraphExecDestroy(gexec); }
 };
 
 struct YoloModel {
@@ -192,11 +199,12 @@ struct YoloModel {
   Arena arena;                 // activation workspace shared by all plans (size of the largest)
   uint64_t tick = 0;
   int sms = 0;
+  cudaStream_t cap_stream = nullptr;   // private stream the graphs are captured on (the caller's may be the legacy default stream)
   // fp32-accurate mode (CC_YOLO_FP32_ACCURATE): activations are stored in fp32 and every conv runs on the same tcgen05 kernel
   // over a 3-way bf16 split of both operands (six plane products, fp32 accumulation): the result carries fp32-level error
   // instead of bf16's 2^-9, at ~6x the tensor work and 2x the activation bytes.  The mode the 1e-3 parity bar is checked in.
   bool precise = false;
-  ~YoloModel() { plans.clear(); for (void* p : allocs) cudaFree(p); }
+  ~YoloModel() { plans.clear(); if (cap_stream) cudaStreamDestroy(cap_stream); for (void* p : allocs) cudaFree(p); }
 
   int upload(const void* h, size_t bytes, void** d) {
     CC_CHECK_CUDA(cudaMalloc(d, bytes));
@@ -927,7 +935,37 @@ int cc_yolo_forward(cc_yolo* h, const void* d_frames, int is_f32, int B, int Hf,
   YoloPlan* P = nullptr;
   int rc = get_plan(h, is_f32, B, Hf, Wf, res, &P);
   if (rc) return rc;
-  return plan_run(*P, d_frames, d_out, d_raw, static_cast<cudaStream_t>(stream));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static const int graph_env = getenv("CC_GRAPH") ? atoi(getenv("CC_GRAPH")) : 1;
+  if (graph_env) {
+    if (P->gexec && P->g_frames == d_frames && P->g_out == d_out && P->g_raw == d_raw) {
+      CC_CHECK_CUDA(cudaGraphLaunch(P->gexec, st));
+      return CC_OK;
+    }
+    const bool stable = P->l_frames == d_frames && P->l_out == d_out && P->l_raw == d_raw;
+    P->l_frames = d_frames; P->l_out = d_out; P->l_raw = d_raw;
+    if (stable) {
+      // second call in a row with these pointers: capture the launch list (on a private stream: nothing executes) and replay
+      if (!h->m.cap_stream) CC_CHECK_CUDA(cudaStreamCreateWithFlags(&h->m.cap_stream, cudaStreamNonBlocking));
+      if (P->gexec) { cudaGraphExecDestroy(P->gexec); P->gexec = nullptr; }
+      cudaGraph_t g = nullptr;
+      bool ok = cudaStreamBeginCapture(h->m.cap_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+      if (ok) {
+        rc = plan_run(*P, d_frames, d_out, d_raw, h->m.cap_stream);
+        ok = cudaStreamEndCapture(h->m.cap_stream, &g) == cudaSuccess && rc == CC_OK && g != nullptr;
+      }
+      if (ok) ok = cudaGraphInstantiate(&P->gexec, g, 0) == cudaSuccess;
+      if (g) cudaGraphDestroy(g);
+      if (ok) {
+        P->g_frames = d_frames; P->g_out = d_out; P->g_raw = d_raw;
+        CC_CHECK_CUDA(cudaGraphLaunch(P->gexec, st));
+        return CC_OK;
+      }
+      cudaGetLastError();            // capture is an optimisation: fall through to plain launches
+      P->gexec = nullptr;
+    }
+  }
+  return plan_run(*P, d_frames, d_out, d_raw, st);
 }
 
 int cc_yolo_plan_info(cc_yolo* h, int is_f32, int B, int Hf, int Wf, int res, int* net_h, int* net_w, int* anchors,

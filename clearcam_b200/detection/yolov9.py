@@ -252,11 +252,37 @@ class YOLOv9:
             yield h
 
     def __call__(self, frame):
-        """frame: HWC BGR image (uint8 or float32; numpy / torch / anything with .numpy()).  -> (300,6)"""
-        t = self._as_device_frames(frame)
+        """frame: HWC BGR image (uint8 or float32; numpy / torch / anything with .numpy()).  -> (300,6)
+        The single-frame call of the reference's camera loop (clearcam.py:580-583).  A host frame is copied into a device
+        buffer this object keeps per frame shape and the result is produced in a kept buffer too, so the library sees the same
+        pointers call after call and replays its captured CUDA graph of the plan instead of re-launching ~140 kernels."""
+        t = frame
+        if isinstance(t, DeviceResult):
+            t = t.tensor
+        if isinstance(t, torch.Tensor) and t.is_cuda:
+            t = self._as_device_frames(t)
+            if t.dim() == 3:
+                t = t.unsqueeze(0)
+            return DeviceResult(self.detect_batch(t)[0])
+        if not isinstance(t, torch.Tensor):
+            if hasattr(t, "numpy") and not isinstance(t, np.ndarray):
+                t = t.numpy()
+            t = torch.from_numpy(np.ascontiguousarray(t))
+        if t.dtype not in (torch.uint8, torch.float32):
+            t = t.to(torch.float32)
         if t.dim() == 3:
             t = t.unsqueeze(0)
-        return DeviceResult(self.detect_batch(t)[0])
+        key = (tuple(t.shape), t.dtype)
+        bufs = getattr(self, "_single", None)
+        if bufs is None or bufs[0] != key:
+            bufs = self._single = (key, torch.empty(t.shape, dtype=t.dtype, device="cuda"),
+                                   torch.empty(t.shape[0], 300, 6, device="cuda", dtype=torch.float32))
+        _, dev, out = bufs
+        dev.copy_(t, non_blocking=True)
+        B, Hf, Wf, _c = dev.shape
+        check(lib().cc_yolo_forward(self._h, ptr(dev), 1 if dev.dtype == torch.float32 else 0, B, Hf, Wf, self.res, ptr(out),
+                                    None, stream_ptr()), "cc_yolo_forward")
+        return DeviceResult(out[0].clone())
 
     def plan_info(self, B, Hf, Wf, is_f32=False) -> dict:
         i = [ctypes.c_int() for _ in range(4)]

@@ -1,0 +1,104 @@
+"""Parity on the configurations bench.py and BASELINE.json name (the smaller cases are in test_yolo_gpu.py / test_clip_gpu.py):
+
+  * YOLOv9-c 640x640 at B=32 (the bench step), YOLOv9-e 640x640 at B=16 (configs[4] per GPU), YOLOv9-c on 1080x1920 frames
+    letterboxed to 384x640 (configs[3]) — sampled frames of the batch against the fp32 CPU oracle;
+  * both detector modes: the default (bf16 activation storage) with p50 / p99 / max bars taken from measurement, and the
+    fp32-accurate mode at the north-star bar (boxes, scores; class ids exact);
+  * CLIP ViT-B/32 at B=256 and ViT-L/14 at B=64, sampled rows against the fp32 oracle.
+
+Bars.  The reference computes in fp32; two fp32 evaluations of the same network already differ by up to 7e-3 px (1 thread vs
+N threads, tests/test_oracle_cpu.py::test_fp32_noise_floor_of_the_reference_arithmetic), so "within 1e-3" is asked of the
+class probabilities and of the box coordinates at p99 <= 1e-2 px; every class id must be identical wherever the oracle's
+confidence passes the 0.25 threshold with a margin above that noise."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import clip as oc
+from oracle import yolov9 as o
+from clearcam_b200.detection.yolov9 import YOLOv9
+from clearcam_b200.models.objects import OpenCLIP
+
+pytestmark = pytest.mark.gpu
+
+CASES = [("c", 640, 32, 640, 640), ("e", 640, 16, 640, 640), ("c", 640, 8, 1080, 1920)]
+# measured on B200 (tests/tools/diag_precise.py), default mode vs fp32 oracle, head output over ALL anchors:
+#   size c: box |d| p50 ~0.1 px, p99 ~2-3.5 px; class prob |d| p99 ~4e-3, max ~0.06 (synthetic weights are far worse
+#   conditioned than trained ones: real YOLOv9-t weights give p90 0.15 px)
+DEFAULT_BARS = {"box_p50": 0.5, "box_p99": 6.0, "prob_p99": 2e-2, "prob_max": 0.15}
+PRECISE_BARS = {"box_p99": 1e-2, "box_max": 0.25, "prob_max": 1e-3}
+
+
+def _frames(B, H, W, seed):
+    base = o.synthetic_frames(4, H, W, seed=seed)
+    return torch.stack([torch.roll(base[i % 4], shifts=(3 * (i // 4), 5 * (i // 4)), dims=(0, 1)) for i in range(B)])
+
+
+def _q(t, p):
+    t = t.flatten()
+    return float(torch.quantile(t[:: max(1, t.numel() // 4000000)], p))
+
+
+@pytest.mark.parametrize("precise", [False, True], ids=["default-bf16", "fp32-accurate"])
+@pytest.mark.parametrize("size,res,B,H,W", CASES)
+def test_detector_on_bench_configs(size, res, B, H, W, precise):
+    fr = _frames(B, H, W, seed=21)
+    sample = sorted({0, B // 3, (2 * B) // 3, B - 1})
+    pre = torch.stack([o.preprocess(fr[i], res) for i in sample])
+    x = pre.flip(-1).permute(0, 3, 1, 2).float() / 255
+    P = o.synthetic_weights(size, seed=21, calib=x[:2])
+    with torch.no_grad():
+        want = o.forward_raw(size, P, x)
+    ref = o.detect(size, P, fr[sample], res)
+    m = YOLOv9(size, res, weights=P, precise=precise)
+    out, raw = m.detect_batch(fr, raw=True)
+    torch.cuda.synchronize()
+    out, raw = out.cpu()[sample], raw.cpu()[sample]
+    assert raw.shape == want.shape
+    db, dp = (raw[:, :4] - want[:, :4]).abs(), (raw[:, 4:] - want[:, 4:]).abs()
+    conf, ids = want[:, 4:].max(1)
+    if precise:
+        assert _q(db, 0.99) <= PRECISE_BARS["box_p99"], f"box p99 {_q(db, 0.99)}"
+        assert float(db.max()) <= PRECISE_BARS["box_max"], f"box max {float(db.max())}"
+        assert float(dp.max()) <= PRECISE_BARS["prob_max"], f"prob max {float(dp.max())}"
+        # class ids: identical for every anchor the oracle keeps (conf >= 0.25) whose top-2 class margin exceeds the noise
+        top2 = want[:, 4:].topk(2, dim=1)[0]
+        sure = (conf >= 0.25) & ((top2[:, 0] - top2[:, 1]) > 2e-3)
+        assert bool((raw[:, 4:].argmax(1)[sure] == ids[sure]).all())
+        # final rows: same detections in the same order (scores equal to 1e-3 cannot reorder rows that differ by more)
+        for b in range(len(sample)):
+            A, G = ref[b][ref[b][:, 4] > 0], out[b][out[b][:, 4] > 0]
+            if len(A) == len(G) and len(A) and bool((A[:, 5] == G[:, 5]).all()):
+                assert float((A[:, :4] - G[:, :4]).abs().max()) <= 0.25 and float((A[:, 4] - G[:, 4]).abs().max()) <= 1e-3
+            else:       # a pair of near-tied scores swapped, or a box at the 0.25 / IoU 0.45 boundary: compare as sets
+                d = (A[:, None, :4] - G[None, :, :4]).abs().max(-1)[0] + (A[:, None, 5] != G[None, :, 5]) * 1e6
+                assert float((d.min(1)[0] < 0.25).float().mean()) >= 0.97, (len(A), len(G))
+    else:
+        assert _q(db, 0.5) <= DEFAULT_BARS["box_p50"] and _q(db, 0.99) <= DEFAULT_BARS["box_p99"], (_q(db, 0.5), _q(db, 0.99))
+        assert _q(dp, 0.99) <= DEFAULT_BARS["prob_p99"] and float(dp.max()) <= DEFAULT_BARS["prob_max"], (_q(dp, 0.99), float(dp.max()))
+        sure = (conf >= 0.3) & ((want[:, 4:].topk(2, dim=1)[0][:, 0] - want[:, 4:].topk(2, dim=1)[0][:, 1]) > 0.1)
+        assert float((raw[:, 4:].argmax(1)[sure] == ids[sure]).float().mean()) >= 0.995
+
+
+@pytest.mark.parametrize("arch,B", [("ViT-B/32", 256), ("ViT-L/14", 64)])
+def test_clip_on_bench_configs(arch, B):
+    cfg = oc.CONFIGS[arch]
+    P = oc.synthetic_weights(cfg, seed=3)
+    x = oc.synthetic_images(8, cfg.image_size, seed=5)[torch.arange(B) % 8]
+    x = x + 0.01 * torch.arange(B).view(B, 1, 1, 1) / B                    # all rows distinct
+    sample = sorted({0, 1, B // 3, B // 2, (2 * B) // 3, B - 2, B - 1})
+    with torch.no_grad():
+        want = oc.encode_image(cfg, P, x[sample])
+    m = OpenCLIP(weights=P, arch=arch)
+    got = m.precompute_embedding(x).tensor.cpu()[sample]
+    cos = (got * want).sum(-1) / (got.norm(dim=-1) * want.norm(dim=-1))
+    assert cos.min() >= 0.999, f"cosine {cos.min()}"
+    assert ((got @ got.T) - (want @ want.T)).abs().max() < 5e-3
+    # text tower at the bench batch (256 queries), sampled
+    g = torch.Generator().manual_seed(1)
+    ids = oc.pad_tokens([torch.randint(1000, 40000, (int(n),), generator=g).tolist() for n in torch.randint(3, 20, (256,), generator=g)])
+    with torch.no_grad():
+        twant = oc.encode_text_ids(cfg, P, ids[sample])
+    tgot = m.encode_token_ids(ids.int()).tensor.cpu()[sample]
+    tcos = (tgot * twant).sum(-1) / (tgot.norm(dim=-1) * twant.norm(dim=-1))
+    assert tcos.min() >= 0.999, f"text cosine {tcos.min()}"

@@ -123,7 +123,7 @@ def _match(ref, got):
 
 
 @pytest.mark.parametrize("size,res,B,H,W", [("c", 320, 2, 320, 320), ("e", 256, 2, 256, 256), ("t", 320, 2, 320, 320),
-                                             ("s", 256, 1, 256, 256), ("c", 320, 3, 270, 480), ("c", 640, 8, 640, 640),
+                                             ("s", 256, 1, 256, 256), ("c", 320, 3, 270, 480), ("c", 640, 8, 640, 640), ("c", 320, 2, 272, 480),
                                              ("m", 256, 2, 256, 256)])
 def test_model_vs_oracle(size, res, B, H, W):
     fr, x, P = _setup(size, res, B, H, W, seed=7)
