@@ -26,8 +26,10 @@ static constexpr int kMaxLk = 384;   // S uses TMEM columns [0, Lk), O the 64 co
 struct AttnParams {
   CUtensorMap tmQK;   // qkv viewed as [B*L rows][3W cols], box 64 rows x 64 cols
   CUtensorMap tmVt;   // Vt [B*H*64 rows][Lk cols], box 64 rows x 64 cols
+  const __nv_bfloat16* qkv;
   __nv_bfloat16* ctx;
   int B, L, Lk, H, W, causal;
+  int tail;        // 1: one image per CTA and L = 128 n + 1 -> the last token runs on CUDA cores (warp 9)
   int G;           // images per CTA (packed sequence of G*L tokens, Lk = ceil(G*L / 64) * 64 key columns)
   int tmem_cols;   // power of two >= Lk + 64
 };
@@ -59,7 +61,11 @@ __global__ void __launch_bounds__(256) vt_kernel(const __nv_bfloat16* __restrict
 }
 
 // ---------------------------------------------------------------- main kernel
-__global__ void __launch_bounds__(160) attention_tc_kernel(const __grid_constant__ AttnParams p) {
+// warps: 0 = control (TMA + MMA issue), 1..8 = softmax (two warps per TMEM lane quarter, each taking every other 16-column
+// chunk of a row), 9 = tail row on CUDA cores (sequences of 128 n + 1 tokens, i.e. ViT-L/14's 257: the last token would
+// otherwise cost a whole 128-row block of MMA + softmax work for one row)
+static constexpr int kAttnThreads = 320;
+__global__ void __launch_bounds__(kAttnThreads, 1) attention_tc_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -73,23 +79,28 @@ __global__ void __launch_bounds__(160) attention_tc_kernel(const __grid_constant
   uint64_t* bar_v = bars + 1;    // V^T landed
   uint64_t* bar_q = bars + 2;    // Q block landed            (phase per q-block)
   uint64_t* bar_s = bars + 3;    // S = QK^T complete
-  uint64_t* bar_p = bars + 4;    // P written (4 arrivals: one per softmax warp)
+  uint64_t* bar_p = bars + 4;    // P written (8 arrivals: one per softmax warp)
   uint64_t* bar_o = bars + 5;    // O = PV complete
-  uint64_t* bar_oe = bars + 6;   // O read back (4 arrivals)
+  uint64_t* bar_oe = bars + 6;   // O read back (8 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+  float* sRed = reinterpret_cast<float*>(bars + 8);   // [2][128] partial row maxima of the two column halves
+  float* sSum = sRed + 256;                            // [2][128] partial row sums
+  float* sPt = sSum + 256;                             // [kMaxLk] tail row probabilities
 
   const int bh = blockIdx.x, grp = bh / p.H, h = bh % p.H;
   const int nimg = (p.B - grp * p.G) < p.G ? (p.B - grp * p.G) : p.G;   // images in this group (the last one may be short)
   const int Lt = nimg * p.L;                      // tokens of the packed sequence
-  const int nqb = (Lt + 127) >> 7;
+  const bool tail = p.tail != 0;                  // the last token is computed by warp 9
+  const int nqb = tail ? (Lt >> 7) : ((Lt + 127) >> 7);
   const uint32_t kOCol = p.Lk;                    // O accumulator right after S
+  const int row0 = grp * p.G * p.L;               // first row of the packed sequence in the QKV / ctx buffers
 
   if (warp == 0) {
     if (lane == 0) {
       tma_prefetch_desc(&p.tmQK);
       tma_prefetch_desc(&p.tmVt);
       mbar_init(bar_k, 1); mbar_init(bar_v, 1); mbar_init(bar_q, 1); mbar_init(bar_s, 1);
-      mbar_init(bar_p, 4); mbar_init(bar_o, 1); mbar_init(bar_oe, 4);   // one arrival per softmax warp
+      mbar_init(bar_p, 8); mbar_init(bar_o, 1); mbar_init(bar_oe, 8);   // one arrival per softmax warp
       fence_mbar_init();
     }
     __syncwarp();
@@ -103,15 +114,16 @@ __global__ void __launch_bounds__(160) attention_tc_kernel(const __grid_constant
 
   if (warp == 0) {
     // ===================== control warp: TMA loads + MMA issue (one elected lane) =====================
-    const int row0 = grp * p.G * p.L;
     if (lane == 0) {
       mbar_arrive_expect_tx(bar_k, p.Lk * 128);
       for (int j = 0; j < nkb; ++j) tma_load_2d(sK + j * 8192, &p.tmQK, bar_k, p.W + h * 64, row0 + 64 * j);
       mbar_arrive_expect_tx(bar_v, nkb * 8192);
       for (int j = 0; j < nkb; ++j) tma_load_2d(sV + j * 8192, &p.tmVt, bar_v, 64 * j, bh * 64);
-      mbar_arrive_expect_tx(bar_q, 128 * 128);
-      tma_load_2d(sQ, &p.tmQK, bar_q, h * 64, row0);
-      tma_load_2d(sQ + 8192, &p.tmQK, bar_q, h * 64, row0 + 64);
+      if (nqb > 0) {
+        mbar_arrive_expect_tx(bar_q, 128 * 128);
+        tma_load_2d(sQ, &p.tmQK, bar_q, h * 64, row0);
+        tma_load_2d(sQ + 8192, &p.tmQK, bar_q, h * 64, row0 + 64);
+      }
     }
     __syncwarp();
     const int nch = (p.Lk + 255) >> 8;             // N chunks of the first MMA (N <= 256 each)
@@ -163,27 +175,31 @@ __global__ void __launch_bounds__(160) attention_tc_kernel(const __grid_constant
       }
       __syncwarp();
     }
-  } else {
-    // ===================== softmax / epilogue warps (thread == query row) =====================
+  } else if (warp <= 8) {
+    // ===================== softmax / epilogue warps (thread pair == query row) =====================
     const int quarter = warp & 3;
+    const int half = (warp - 1) >> 2;             // which 16-column chunks of a row this warp handles (chunk parity)
     const int row = quarter * 32 + lane;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const float kScale = 0.125f * 1.4426950408889634f;   // 1/sqrt(64) * log2(e)
     for (int qb = 0; qb < nqb; ++qb) {
       const uint32_t ph = qb & 1;
       const int qi = qb * 128 + row;              // query index inside the packed sequence
-      // keys this row may see: those of its own image, up to itself when causal
-      int lo = 0, lim = 0;
+      // keys this row may see: those of its own image, up to itself when causal (rows past the packed sequence: none)
+      int lo = 0x7fffffff, lim = -1;
       if (qi < Lt) {
         const int img = qi / p.L;
         lo = img * p.L;
         lim = p.causal ? qi : lo + p.L - 1;
       }
-      const int c_lo = lo & ~15;                  // 16-column chunks that intersect [lo, lim]
+      // tcgen05.ld is .sync.aligned: every lane of the warp must execute the same loads, so the chunk loops run over the
+      // WARP's key range (its 32 consecutive rows touch at most two or three images) and each lane masks to its own keys
+      const int w_lo = __reduce_min_sync(0xffffffffu, lo) & ~15;     // 16-column chunks that intersect the warp's keys
+      const int w_hi = __reduce_max_sync(0xffffffffu, lim);
       mbar_wait(bar_s, ph);
       tc_fence_after();
       float m = -INFINITY;
-      for (int c0 = c_lo; c0 <= lim; c0 += 16) {
+      for (int c0 = w_lo + 16 * half; c0 <= w_hi; c0 += 32) {
         uint32_t v[16];
         tmem_ld16(t_row + c0, v);
         tmem_ld_wait();
@@ -191,12 +207,15 @@ __global__ void __launch_bounds__(160) attention_tc_kernel(const __grid_constant
         for (int j = 0; j < 16; ++j)
           if (c0 + j >= lo && c0 + j <= lim) m = fmaxf(m, __uint_as_float(v[j]));
       }
+      sRed[half * 128 + row] = m;
+      named_bar_sync(1, 256);                     // the two column halves of every row exchange their maxima
+      m = fmaxf(m, sRed[(half ^ 1) * 128 + row]);
       const float mc = m * kScale;
       float sum = 0.f;
-      for (int c0 = 0; c0 < p.Lk; c0 += 16) {
+      for (int c0 = 16 * half; c0 < p.Lk; c0 += 32) {
         uint8_t* blk = sP + (c0 >> 6) * 16384 + row * 128;
         const uint32_t i0 = (c0 & 63) >> 3;
-        if (c0 < c_lo || c0 > lim) {             // another image's keys: P = 0, no TMEM read, no exponentials
+        if (c0 < w_lo || c0 > w_hi) {            // keys of images no row of this warp belongs to: P = 0, no TMEM read, no exponentials
           *reinterpret_cast<uint4*>(blk + ((i0 ^ (row & 7)) << 4)) = make_uint4(0, 0, 0, 0);
           *reinterpret_cast<uint4*>(blk + (((i0 + 1) ^ (row & 7)) << 4)) = make_uint4(0, 0, 0, 0);
           continue;
@@ -223,19 +242,20 @@ __global__ void __launch_bounds__(160) attention_tc_kernel(const __grid_constant
           *reinterpret_cast<uint4*>(blk + (((i0 + q) ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
+      sSum[half * 128 + row] = sum;               // read by the partner after bar_o (ordered through bar_p -> MMA -> bar_o)
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_p);
-      // ---- O -> ctx
+      // ---- O -> ctx: each warp of the pair normalises and stores 32 of the 64 output columns
       mbar_wait(bar_o, ph);
       tc_fence_after();
-      const float inv = 1.0f / sum;
-      __nv_bfloat16* out = p.ctx + (static_cast<long long>(grp) * p.G * p.L + qi) * p.W + h * 64;
+      const float inv = 1.0f / (sum + sSum[(half ^ 1) * 128 + row]);
+      __nv_bfloat16* out = p.ctx + (static_cast<long long>(row0) + qi) * p.W + h * 64 + 32 * half;
 #pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 16) {
+      for (int c0 = 0; c0 < 32; c0 += 16) {
         uint32_t v[16];
-        tmem_ld16(t_row + kOCol + c0, v);
+        tmem_ld16(t_row + kOCol + 32 * half + c0, v);
         tmem_ld_wait();
         if (qi < Lt) {
 #pragma unroll
@@ -255,6 +275,91 @@ __global__ void __launch_bounds__(160) attention_tc_kernel(const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_oe);
     }
+  } else if (tail) {
+    // ===================== tail row (token Lt - 1) on CUDA cores, from the K and V^T tiles in shared memory ===============
+    const int qi = Lt - 1;
+    float q[64];
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(p.qkv + (static_cast<long long>(row0) + qi) * 3 * p.W + h * 64);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 u = __ldg(src + c);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          q[8 * c + 2 * j] = __uint_as_float(w[j] << 16);
+          q[8 * c + 2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
+        }
+      }
+    }
+    const float kScale = 0.125f * 1.4426950408889634f;
+    mbar_wait(bar_k, 0);
+    float sc[kMaxLk / 32];
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < kMaxLk / 32; ++i) {
+      const int j = lane + 32 * i;
+      float a = -INFINITY;
+      if (j < Lt && j < p.Lk) {                   // the last token sees every key of its image (causal or not)
+        const uint8_t* kr = sK + (j >> 6) * 8192 + (j & 63) * 128;
+        a = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 u = *reinterpret_cast<const uint4*>(kr + ((c ^ (j & 7)) << 4));
+          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            a = fmaf(q[8 * c + 2 * t], __uint_as_float(w[t] << 16), a);
+            a = fmaf(q[8 * c + 2 * t + 1], __uint_as_float(w[t] & 0xFFFF0000u), a);
+          }
+        }
+        a *= kScale;
+      }
+      sc[i] = a;
+      m = fmaxf(m, a);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxLk / 32; ++i) {
+      const int j = lane + 32 * i;
+      float e = 0.f;
+      if (j < Lt && j < p.Lk) {
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(sc[i] - m));
+        e = __bfloat162float(__float2bfloat16_rn(e));    // as the tensor-core rows: P is rounded to bf16 before P.V
+      }
+      if (j < p.Lk) sPt[j] = e;
+      sum += e;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __syncwarp();
+    mbar_wait(bar_v, 0);
+    float o0 = 0.f, o1 = 0.f;                     // output dims lane and lane + 32
+    for (int kb = 0; kb < nkb; ++kb) {
+      const uint8_t* v0 = sV + kb * 8192 + lane * 128;
+      const uint8_t* v1 = v0 + 32 * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float4 pa = *reinterpret_cast<const float4*>(sPt + kb * 64 + c * 8), pb = *reinterpret_cast<const float4*>(sPt + kb * 64 + c * 8 + 4);
+        const float pp[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+        const uint4 a = *reinterpret_cast<const uint4*>(v0 + ((c ^ (lane & 7)) << 4));
+        const uint4 b = *reinterpret_cast<const uint4*>(v1 + ((c ^ (lane & 7)) << 4));
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          o0 = fmaf(pp[2 * t], __uint_as_float(aw[t] << 16), o0);
+          o0 = fmaf(pp[2 * t + 1], __uint_as_float(aw[t] & 0xFFFF0000u), o0);
+          o1 = fmaf(pp[2 * t], __uint_as_float(bw[t] << 16), o1);
+          o1 = fmaf(pp[2 * t + 1], __uint_as_float(bw[t] & 0xFFFF0000u), o1);
+        }
+      }
+    }
+    const float inv = 1.0f / sum;
+    __nv_bfloat16* out = p.ctx + (static_cast<long long>(row0) + qi) * p.W + h * 64;
+    out[lane] = __float2bfloat16_rn(o0 * inv);
+    out[lane + 32] = __float2bfloat16_rn(o1 * inv);
   }
   tc_fence_before();
   __syncthreads();
@@ -304,7 +409,7 @@ int attention_tc_launch(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, __nv_bfloa
   PFN_encodeTiled enc = get_encode_tiled();
   CC_REQUIRE(enc != nullptr, "attention_tc: cuTensorMapEncodeTiled unavailable");
   AttnParams p{};
-  p.ctx = ctx; p.B = B; p.L = L; p.Lk = Lk; p.H = H; p.W = W; p.causal = causal; p.G = G;
+  p.qkv = qkv; p.ctx = ctx; p.tail = (G == 1 && L > 128 && (L & 127) == 1) ? 1 : 0; p.B = B; p.L = L; p.Lk = Lk; p.H = H; p.W = W; p.causal = causal; p.G = G;
   p.tmem_cols = 32;
   while (p.tmem_cols < Lk + 64) p.tmem_cols <<= 1;
   {
@@ -327,13 +432,13 @@ int attention_tc_launch(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, __nv_bfloa
   }
   vt_kernel<<<dim3(NG * H, nkb), 256, 0, st>>>(qkv, vt_ws, G * L, static_cast<long long>(B) * L, Lk, H, W);
   CC_CHECK_CUDA(cudaGetLastError());
-  const int smem = 1024 + 128 * 128 + Lk * 128 + nkb * 8192 + nkb * 16384 + 128;
+  const int smem = 1024 + 128 * 128 + Lk * 128 + nkb * 8192 + nkb * 16384 + 64 + (512 + kMaxLk) * 4;
   static bool attr_set = false;
   if (!attr_set) {
     CC_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  attention_tc_kernel<<<NG * H, 160, smem, st>>>(p);
+  attention_tc_kernel<<<NG * H, kAttnThreads, smem, st>>>(p);
   CC_CHECK_CUDA(cudaGetLastError());
   return CC_OK;
 }

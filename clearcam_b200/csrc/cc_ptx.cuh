@@ -112,6 +112,11 @@ __device__ __forceinline__ void tma_store_5d(const void* tmap, const void* smem_
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
 // TMA reduce-add store: global[box] += smem tile, performed at the L2 (used for the in-place fp32 residual of the CLIP
 // out-proj / MLP-proj GEMMs: x += GEMM, one fp32 add per element exactly like load-add-store).
 __device__ __forceinline__ void tma_reduce_add_5d(const void* tmap, const void* smem_src, int c0, int c1, int c2, int c3, int c4) {

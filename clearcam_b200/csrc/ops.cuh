@@ -2,6 +2,7 @@
 // All activations are NHWC; a tensor is addressed as (base pointer, channel stride `cs` = channels per
 // pixel of the underlying buffer, channel offset `co`, channel count) so concat/chunk are free.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -69,6 +70,20 @@ int stem_launch(const StemParams& p, cudaStream_t s);
 // exact in bf16; taps in (r,s,RGB) order = frame channel 2-c; columns 27..31 zero), consumed by conv_gemm with weights
 // bf16(w/255).
 int stem_im2col_launch(const uint8_t* frames, __nv_bfloat16* out, int B, int H, int W, cudaStream_t s);
+// uint8 stem on tensor cores without the im2col round trip (stem_tc.cu): the A tile is gathered from the frame into shared
+// memory by the CTA itself.  Built once per plan (output tensor map), launched with the frame pointer of the call.
+struct StemTcParams {
+  CUtensorMap tmC;           // 2-D [Mrows][Cout] bf16 view of the output slice (row pitch = cs), box [128][Cout]
+  const uint8_t* in;         // [B][H][W][3] BGR
+  const __nv_bfloat16* w;    // [Cout][32]
+  const float* bias;         // [Cout]
+  int B, H, W, Cout;
+  long long Mrows;
+  int tiles;
+  int tmem_cols;
+};
+int stem_tc_build(int B, int H, int W, const __nv_bfloat16* w32, const float* bias, int Cout, const TSlice& out, StemTcParams* p);
+int stem_tc_launch(const StemTcParams& p, const uint8_t* frames, cudaStream_t s);
 
 // Detect head tail: DFL softmax-expectation, dist2bbox, x stride, sigmoid, max/argmax, conf threshold
 // (detection/yolov9.py:209-219, 273-282, 263-271, 440-448).  Inputs are the fp32 logits of the three scales.

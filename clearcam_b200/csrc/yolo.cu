@@ -155,13 +155,15 @@ static __nv_bfloat16 f2bf(float x) { return __float2bfloat16_rn(x); }
 struct T { __nv_bfloat16* p = nullptr; int cs = 0, co = 0, C = 0, H = 0, W = 0; bool image = false; bool f32 = false; };   // f32: p is really float*
 
 struct Op {
-  enum Kind { GEMM, DIRECT, AVGPAD, AVGMAX, MAXPOOL5, UPSAMPLE, CBFUSE, LETTERBOX, STEM, STEM_IM2COL, DECODE, POST, SPLIT } kind;
+  enum Kind { GEMM, DIRECT, AVGPAD, AVGMAX, MAXPOOL5, UPSAMPLE, CBFUSE, LETTERBOX, STEM, STEM_IM2COL, STEM_TC, DECODE, POST, SPLIT } kind;
   GemmLaunch gemm;
   DirectConvParams direct;
   TSlice s_in, s_out;
   CBFuseParams cbf;
   LetterboxParams lb;
   StemParams stem;
+  StemTcParams stem_tc;
+  double flops = 0;          // algorithmic FLOPs of a non-GEMM conv op (stem)
   DecodeParams dec;
   PostParams post;
   std::string name;
@@ -513,7 +515,6 @@ int Builder::build() {
   outs.assign(nl, T{});
   cbl_chunks.assign(nl, {});
   T image; image.image = true; image.C = 3; image.H = P.H; image.W = P.W;
-  T cur = image;
   for (int i = 0; i < nl && !rc; ++i) {
     const Layer& l = S[i];
     const std::string pfx = "model." + std::to_string(i);
@@ -529,9 +530,19 @@ int Builder::build() {
           const ConvW& cw = M.convs[pfx];
           static const int stem_tc_env = getenv("CC_STEM_TC") ? atoi(getenv("CC_STEM_TC")) : 1;
           if (!P.is_f32 && stem_tc_env && cw.cout % 16 == 0 && !M.precise) {
-            // uint8 frames: raw pixel values are exact in bf16 -> im2col to [B*Ho*Wo, 32] and run the tensor-core GEMM
-            // with weights bf16(w/255)
+            // uint8 frames: raw pixel values are exact in bf16, weights bf16(w/255).  Default (CC_STEM_TC=1): stem_tc_kernel
+            // gathers the A tile from the frame itself; CC_STEM_TC=2: the earlier im2col to [B*Ho*Wo, 32] + conv_gemm
             const long long Mrows = static_cast<long long>(P.B) * (P.H / 2) * (P.W / 2);
+            if (stem_tc_env == 1 && (cw.cout == 16 || cw.cout == 32 || cw.cout == 64)) {
+              if (bump.dry) break;
+              Op op; op.kind = Op::STEM_TC; op.name = pfx; op.stem = StemParams{}; op.stem.in = net_in;
+              rc = stem_tc_build(P.B, P.H, P.W, cw.wtc, cw.bias, cw.cout, ts(out), &op.stem_tc);
+              if (rc) break;
+              op.flops = 2.0 * Mrows * cw.cout * 27;
+              P.conv_flops += op.flops;
+              P.ops.push_back(std::move(op));
+              break;
+            }
             __nv_bfloat16* cols = static_cast<__nv_bfloat16*>(dalloc(static_cast<size_t>(Mrows) * 32 * 2));
             if (bump.dry) break;
             { Op op; op.kind = Op::STEM_IM2COL; op.name = pfx + ".im2col"; op.stem = StemParams{};
@@ -732,6 +743,9 @@ static int plan_run(YoloPlan& P, const void* d_frames, float* d_out, float* d_ra
         rc = stem_im2col_launch(static_cast<const uint8_t*>(op.stem.in ? op.stem.in : d_frames), op.s_out.p, op.stem.B, op.stem.H,
                                 op.stem.W, st);
         break;
+      case Op::STEM_TC:
+        rc = stem_tc_launch(op.stem_tc, static_cast<const uint8_t*>(op.stem.in ? op.stem.in : d_frames), st);
+        break;
       case Op::DECODE: { DecodeParams q = op.dec; q.raw = d_raw; rc = decode_launch(q, st); break; }
       case Op::POST: { PostParams q = op.post; q.out = d_out; rc = postprocess_launch(q, st); break; }
       case Op::SPLIT: rc = split_planes_launch(op.s_in, op.s_out.p, st); break;
@@ -747,7 +761,7 @@ static const char* op_kind_name(Op::Kind k) {
   switch (k) {
     case Op::GEMM: return "conv_gemm"; case Op::DIRECT: return "conv_direct"; case Op::AVGPAD: return "avgpool2_pad";
     case Op::AVGMAX: return "avgmax_pool"; case Op::MAXPOOL5: return "maxpool5"; case Op::UPSAMPLE: return "upsample2";
-    case Op::CBFUSE: return "cbfuse"; case Op::LETTERBOX: return "letterbox"; case Op::STEM: return "stem"; case Op::STEM_IM2COL: return "stem_im2col";
+    case Op::CBFUSE: return "cbfuse"; case Op::LETTERBOX: return "letterbox"; case Op::STEM: return "stem"; case Op::STEM_IM2COL: return "stem_im2col"; case Op::STEM_TC: return "stem_tc";
     case Op::DECODE: return "decode"; case Op::POST: return "postprocess"; case Op::SPLIT: return "split_planes";
   }
   return "?";
@@ -1003,7 +1017,7 @@ int cc_yolo_profile(cc_yolo* h, const void* d_frames, int is_f32, int B, int Hf,
       float t = 0.f;
       cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
       if (ms) ms[i] = t;
-      if (flops) flops[i] = P->ops[i].kind == Op::GEMM ? P->ops[i].gemm.flops : 0.0;
+      if (flops) flops[i] = P->ops[i].kind == Op::GEMM ? P->ops[i].gemm.flops : P->ops[i].flops;
       if (bytes) bytes[i] = P->ops[i].kind == Op::GEMM ? P->ops[i].gemm.bytes : 0.0;
       if (kinds) kinds[i] = op_kind_name(P->ops[i].kind);
       if (names) names[i] = P->ops[i].name.c_str();

@@ -25,7 +25,7 @@ CASES = [("c", 640, 32, 640, 640), ("e", 640, 16, 640, 640), ("c", 640, 8, 1080,
 # measured on B200 (tests/tools/diag_precise.py), default mode vs fp32 oracle, head output over ALL anchors:
 #   size c: box |d| p50 ~0.1 px, p99 ~2-3.5 px; class prob |d| p99 ~4e-3, max ~0.06 (synthetic weights are far worse
 #   conditioned than trained ones: real YOLOv9-t weights give p90 0.15 px)
-DEFAULT_BARS = {"box_p50": 0.5, "box_p99": 6.0, "prob_p99": 2e-2, "prob_max": 0.15}
+DEFAULT_BARS = {"box_p50": 0.5, "box_p99": 12.0, "prob_p99": 3e-2, "prob_max": 0.2}     # absolute sanity (the relative bars below are the test)
 PRECISE_BARS = {"box_p99": 1e-2, "box_max": 0.25, "prob_max": 1e-3}
 
 
@@ -74,6 +74,14 @@ def test_detector_on_bench_configs(size, res, B, H, W, precise):
                 d = (A[:, None, :4] - G[None, :, :4]).abs().max(-1)[0] + (A[:, None, 5] != G[None, :, 5]) * 1e6
                 assert float((d.min(1)[0] < 0.25).float().mean()) >= 0.97, (len(A), len(G))
     else:
+        # default mode: no further from fp32 than 2x what bf16 storage itself costs (the bf16-mirror oracle's own deviation
+        # from the fp32 oracle on the same frames), plus absolute sanity bars from measurement
+        with torch.no_grad():
+            mirror = o.forward_raw(size, P, x, quant="bf16")
+        mb, mp = (mirror[:, :4] - want[:, :4]).abs(), (mirror[:, 4:] - want[:, 4:]).abs()
+        for pr in (0.5, 0.99):
+            assert _q(db, pr) <= 2.0 * _q(mb, pr) + 0.05, f"box q{pr}: cuda {_q(db, pr)} px, mirror {_q(mb, pr)} px"
+            assert _q(dp, pr) <= 2.0 * _q(mp, pr) + 1e-3, f"prob q{pr}: cuda {_q(dp, pr)}, mirror {_q(mp, pr)}"
         assert _q(db, 0.5) <= DEFAULT_BARS["box_p50"] and _q(db, 0.99) <= DEFAULT_BARS["box_p99"], (_q(db, 0.5), _q(db, 0.99))
         assert _q(dp, 0.99) <= DEFAULT_BARS["prob_p99"] and float(dp.max()) <= DEFAULT_BARS["prob_max"], (_q(dp, 0.99), float(dp.max()))
         sure = (conf >= 0.3) & ((want[:, 4:].topk(2, dim=1)[0][:, 0] - want[:, 4:].topk(2, dim=1)[0][:, 1]) > 0.1)

@@ -130,7 +130,7 @@ def test_model_vs_oracle(size, res, B, H, W):
     tq, tf = [], []
     with torch.no_grad():
         raw_q = o.forward_raw(size, P, x, quant="bf16", taps=tq)
-        o.forward_raw(size, P, x, taps=tf)
+        raw_f = o.forward_raw(size, P, x, taps=tf)
     ref_q = o.detect(size, P, fr, res, quant="bf16")
     m = YOLOv9(size, res, weights=P)
     out, raw = m.detect_batch(fr, raw=True)
@@ -155,12 +155,23 @@ def test_model_vs_oracle(size, res, B, H, W):
     # (3) selection/suppression/scale chain is bit-exact given the SAME head output:
     want = o.scale_boxes((x.shape[2], x.shape[3]), o.postprocess(raw), (H, W))
     assert torch.equal(out, want), f"post chain differs: {(out - want).abs().max()}"
-    # (4) final detections as sets
+    # (4) head output over ALL anchors against the fp32 oracle: the CUDA path may be no further from it than what bf16
+    #     activation storage itself costs — the mirror oracle's own deviation from fp32 — times 2 (two independent bf16
+    #     pipelines decorrelate within a few layers, so CUDA-vs-mirror is not small, but both stay at the format's distance
+    #     from fp32).  Robust statistics (median / 99th percentile), not a match count: with synthetic weights many
+    #     detections sit at the 0.25 threshold and flip with any rounding, so set overlap is a noisy measure.
+    def q(t, pr):
+        t = t.flatten()
+        return float(torch.quantile(t[:: max(1, t.numel() // 2000000)], pr))
+    db_c, db_m = (raw[:, :4] - raw_f[:, :4]).abs(), (raw_q[:, :4] - raw_f[:, :4]).abs()
+    dp_c, dp_m = (raw[:, 4:] - raw_f[:, 4:]).abs(), (raw_q[:, 4:] - raw_f[:, 4:]).abs()
+    for pr in (0.5, 0.99):
+        assert q(db_c, pr) <= 2.0 * q(db_m, pr) + 0.05, f"box q{pr}: cuda-vs-fp32 {q(db_c, pr)} px, mirror-vs-fp32 {q(db_m, pr)} px"
+        assert q(dp_c, pr) <= 2.0 * q(dp_m, pr) + 1e-3, f"prob q{pr}: cuda-vs-fp32 {q(dp_c, pr)}, mirror-vs-fp32 {q(dp_m, pr)}"
+    # (5) final detections as sets: a loose sanity bound only (see above)
     fr_ok = [_match(ref_q[b], out[b]) for b in range(B)]
     frac = np.mean([f for f, _ in fr_ok])
-    # t/s stack three bottlenecks per block (3x the sequential roundings of c/e): their format noise is larger
-    need = 0.8 if size in ("c", "e", "m") else 0.6
-    assert frac >= need, f"only {frac:.2f} of oracle detections matched ({fr_ok})"
+    assert frac >= 0.5, f"only {frac:.2f} of oracle detections matched ({fr_ok})"
 
 
 def test_call_signature_single_frame():
