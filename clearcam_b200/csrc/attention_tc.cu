@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tc_kernel(const __g
       const uint32_t ph = qb & 1;
       const int qi = qb * 128 + row;              // query index inside the packed sequence
       // keys this row may see: those of its own image, up to itself when causal (rows past the packed sequence: none)
-      int lo = 0x7fffffff, lim = -1;
+      int lo = 1 << 28, lim = -1;                 // (sentinel far below INT_MAX: w_lo + 16 must not overflow)
       if (qi < Lt) {
         const int img = qi / p.L;
         lo = img * p.L;

@@ -100,6 +100,8 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+__device__ __forceinline__ int lane_id() { return static_cast<int>(threadIdx.x & 31); }
+
 // ---- MMA issuer role (warp 1), templated on the number of UMMA_K=16 steps per k-block and on resident weights so the
 // issue sequence is straight-line code.  The WHOLE warp runs the loop with warp-uniform values and one elected lane
 // issues: descriptors and TMEM addresses then live in uniform registers (a single active lane made ptxas wrap every
@@ -138,6 +140,7 @@ __device__ __forceinline__ void mma_issuer(const GemmParams& p, uint8_t* sA, uin
     const int n_acc = p.n_acc;
     const uint32_t acc_cols = kTmemCols / n_acc;
     if (BRES) { mbar_wait(bres_bar, 0); tc_fence_after(); }
+    bool first = p.trace != nullptr && blockIdx.x == 0;          // timeline of CTA 0 (cc_yolo_trace): first operands landed
     if (p.halo) {
       int sa = 0;
       uint32_t pa = 0;
@@ -151,6 +154,7 @@ __device__ __forceinline__ void mma_issuer(const GemmParams& p, uint8_t* sA, uin
         for (int ch = 0; ch < cpt; ++ch) {
           mbar_wait(&afull_bar[sa], pa);
           tc_fence_after();
+          if (first) { first = false; if (lane_id() == 0) p.trace[3] = globaltimer_ns(); }
           const uint64_t a_base = d_halo | (sA16 + sa * h16);
           if (BRES) {
             if (elect_one()) {
@@ -202,6 +206,7 @@ __device__ __forceinline__ void mma_issuer(const GemmParams& p, uint8_t* sA, uin
             if (++s2 == S) { s2 = 0; ph2 ^= 1; }
           }
           tc_fence_after();
+          if (first) { first = false; if (lane_id() == 0) p.trace[3] = globaltimer_ns(); }
           if (elect_one()) {
             int s3 = stage;
 #pragma unroll
@@ -221,6 +226,7 @@ __device__ __forceinline__ void mma_issuer(const GemmParams& p, uint8_t* sA, uin
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
+            if (first) { first = false; if (lane_id() == 0) p.trace[3] = globaltimer_ns(); }
             if (elect_one()) {
               mma_kblock<KPB>(d_tmem, d_tile | (sA16 + stage * a16), d_tile | (sB16 + (BRES ? kb : stage) * b16), idesc,
                               static_cast<uint32_t>(kb != 0));
@@ -235,6 +241,7 @@ __device__ __forceinline__ void mma_issuer(const GemmParams& p, uint8_t* sA, uin
         if (++acc == n_acc) { acc = 0; acc_phase ^= 1; }
       }
     }
+    if (p.trace != nullptr && blockIdx.x == 0 && lane_id() == 0) p.trace[4] = globaltimer_ns();   // all MMAs of CTA 0 issued
 }
 
 template <int ACT, bool F32>
@@ -455,6 +462,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 
       mbar_wait(&tfull_bar[grp], tcount & 1);
       tc_fence_after();
+      if (p.trace != nullptr && blockIdx.x == 0 && gt == 0 && grp == 0 && tcount == 0) p.trace[5] = globaltimer_ns();   // first accumulator complete
       if (p.dbg & 1) {
         tc_fence_before();
         __syncwarp();
@@ -618,6 +626,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       }
     }
     if (p.tma_store && gt == 0) tma_store_wait_read<0>();   // smem must outlive the bulk stores' reads (global completion is tracked by the grid)
+    if (p.trace != nullptr && blockIdx.x == 0 && gt == 0) atomicMax(p.trace + 6, globaltimer_ns());   // last epilogue group of CTA 0 done
   }
 
   tc_fence_before();
@@ -627,7 +636,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
-  if (p.trace && threadIdx.x == 0) atomicMax(p.trace + 2, globaltimer_ns());
+  if (p.trace && threadIdx.x == 0) {
+    atomicMax(p.trace + 2, globaltimer_ns());
+    if (blockIdx.x == 0) p.trace[7] = globaltimer_ns();
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -872,7 +884,9 @@ budget_again:
   }
   static const int hst_env = getenv("CC_HALO_STAGES") ? atoi(getenv("CC_HALO_STAGES")) : 0;
   const int bres_bytes = BN * p.BK * 2 * p.num_taps * p.chunks_per_tap;
-  p.b_res = (bres_env && p.n_blocks == 1 && bres_bytes <= 80 * 1024) ? 1 : 0;
+  // resident weights up to 128 KB (a 1x1 conv 256 -> 256): with the halved staging of level 1 four activation stages still fit
+  static const int bres_kb_env = getenv("CC_BRES_KB") ? atoi(getenv("CC_BRES_KB")) : 128;
+  p.b_res = (bres_env && p.n_blocks == 1 && bres_bytes <= bres_kb_env * 1024) ? 1 : 0;
   p.halo_stages = 2;
   if (p.halo) {
     const int b_bytes = BN * p.BK * 2;

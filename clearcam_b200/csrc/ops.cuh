@@ -36,6 +36,15 @@ struct TSlice {
 // the six products with combined weight >= 2^-16 of an fp32 x fp32 product, smallest first.  out: dense [N*H*W][6*C] bf16.
 int split_planes_launch(const TSlice& in, __nv_bfloat16* out, cudaStream_t s);
 
+// fp32-accurate mode, last pass of a conv: out = [res +] act(acc + bias) over npix x C; acc dense [npix][C]; out / res fp32 slices
+struct FinishParams {
+  const float* acc; const float* bias; int act;
+  long long npix; int C;
+  float* out; int out_cs, out_co;
+  const float* res; int res_cs, res_co;
+};
+int finish_f32_launch(const FinishParams& p, cudaStream_t s);
+
 // avg_pool2d(k=2,s=1,p=0) written into a same-size map whose last row/col are zero (so the stride-2 conv that
 // follows can use the even "pixel pair" TMA view).  detection/yolov9.py:47 (ADown), :62 (AConv).
 int avgpool2_pad_launch(const TSlice& in, const TSlice& out, cudaStream_t s);

@@ -145,7 +145,14 @@ struct ConvW {           // device-resident, kernel layout
   __nv_bfloat16* w = nullptr;   // [Cout][k][k][Cin_eff]  (Cin_eff = Cin when dense, Cin/groups when grouped)
   float* wf32 = nullptr;        // stem only: fp32 [Cout][3][3][3]
   __nv_bfloat16* wtc = nullptr; // stem only: bf16 [Cout][32] = w/255 in (r,s,c) order, zero padded (tensor-core uint8 path)
-  __nv_bfloat16* w6 = nullptr;  // fp32-accurate mode: [Cout][k][k][6][Cin_eff] = planes hi|mid|lo|hi|mid|hi of the fp32 weight
+  // fp32-accurate mode: the fp32 weight is split w = hi + mid + lo (three bf16).  w5: [Cout][k][k][5][Cin] = planes
+  // hi|mid|lo|hi|mid (the five cross products below 2^-8 of the result, against the activation planes lo|mid|hi|mid|hi);
+  // whi[i]: [Cout][k][k][seg_c[i]] = the hi plane of input-channel segment i (the hi x hi products, one GEMM per segment so
+  // that no TMEM accumulator takes more than ~48 MMA steps: the tensor core's fp32 accumulation truncates, and its bias
+  // grows with the number of steps into one accumulator — tests/tools/diag_tc_accum.py)
+  __nv_bfloat16* w5 = nullptr;
+  std::vector<__nv_bfloat16*> whi;
+  std::vector<int> seg_off, seg_c;
   float* bias = nullptr;
   int cin = 0, cout = 0, k = 0, groups = 1;   // groups == 1 -> dense (possibly block-diagonal expansion)
 };
@@ -155,7 +162,7 @@ static __nv_bfloat16 f2bf(float x) { return __float2bfloat16_rn(x); }
 struct T { __nv_bfloat16* p = nullptr; int cs = 0, co = 0, C = 0, H = 0, W = 0; bool image = false; bool f32 = false; };   // f32: p is really float*
 
 struct Op {
-  enum Kind { GEMM, DIRECT, AVGPAD, AVGMAX, MAXPOOL5, UPSAMPLE, CBFUSE, LETTERBOX, STEM, STEM_IM2COL, STEM_TC, DECODE, POST, SPLIT } kind;
+  enum Kind { GEMM, DIRECT, AVGPAD, AVGMAX, MAXPOOL5, UPSAMPLE, CBFUSE, LETTERBOX, STEM, STEM_IM2COL, STEM_TC, DECODE, POST, SPLIT, FINISH } kind;
   GemmLaunch gemm;
   DirectConvParams direct;
   TSlice s_in, s_out;
@@ -163,6 +170,7 @@ struct Op {
   LetterboxParams lb;
   StemParams stem;
   StemTcParams stem_tc;
+  FinishParams fin;
   double flops = 0;          // algorithmic FLOPs of a non-GEMM conv op (stem)
   DecodeParams dec;
   PostParams post;
@@ -263,9 +271,15 @@ struct YoloModel {
     }
     else if (!precise) { if ((rc = upload(w.data(), w.size() * 2, reinterpret_cast<void**>(&cw.w)))) return rc; }
     else {
-      // the fp32 weights again (w above is already rounded): planes [hi | mid | lo | hi | mid | hi] per filter tap, matching the
-      // activation planes [lo | mid | hi | mid | hi | hi] written by split_planes_kernel
-      std::vector<__nv_bfloat16> w6(w.size() * 6, f2bf(0.f));
+      // the fp32 weights again (w above is already rounded = the hi plane)
+      {
+        const int steps = cin_eff * k * k / 16;
+        const int nseg = (steps + 47) / 48;
+        const int unit = cin_eff % 64 == 0 ? 64 : 16;
+        int sc = ((cin_eff + nseg - 1) / nseg + unit - 1) / unit * unit;
+        for (int off = 0; off < cin_eff; off += sc) { cw.seg_off.push_back(off); cw.seg_c.push_back(std::min(sc, cin_eff - off)); }
+      }
+      std::vector<__nv_bfloat16> w5(w.size() * 5, f2bf(0.f));
       int cb = 0;
       for (size_t t = 0; t < names.size(); ++t) {
         const float* src = host.find(names[t] + ".weight")->second.p;
@@ -281,13 +295,22 @@ struct YoloModel {
                 const __nv_bfloat16 mid = f2bf(r1);
                 const __nv_bfloat16 lo = f2bf(r1 - __bfloat162float(mid));
                 const int ci_eff = dense ? g * cin_g + ci : ci;
-                __nv_bfloat16* d6 = &w6[(((static_cast<size_t>(cb + co) * k + r) * k + s2) * 6) * cin_eff + ci_eff];
-                d6[0] = hi; d6[cin_eff] = mid; d6[2 * cin_eff] = lo; d6[3 * cin_eff] = hi; d6[4 * cin_eff] = mid; d6[5 * cin_eff] = hi;
+                __nv_bfloat16* d5 = &w5[(((static_cast<size_t>(cb + co) * k + r) * k + s2) * 5) * cin_eff + ci_eff];
+                d5[0] = hi; d5[cin_eff] = mid; d5[2 * cin_eff] = lo; d5[3 * cin_eff] = hi; d5[4 * cin_eff] = mid;
               }
         }
         cb += cout;
       }
-      if ((rc = upload(w6.data(), w6.size() * 2, reinterpret_cast<void**>(&cw.w6)))) return rc;
+      if ((rc = upload(w5.data(), w5.size() * 2, reinterpret_cast<void**>(&cw.w5)))) return rc;
+      for (size_t sgi = 0; sgi < cw.seg_off.size(); ++sgi) {
+        const int off = cw.seg_off[sgi], sc = cw.seg_c[sgi];
+        std::vector<__nv_bfloat16> ws(static_cast<size_t>(cout_total) * k * k * sc);
+        for (size_t row = 0; row < static_cast<size_t>(cout_total) * k * k; ++row)
+          for (int c = 0; c < sc; ++c) ws[row * sc + c] = w[row * cin_eff + off + c];
+        __nv_bfloat16* dptr = nullptr;
+        if ((rc = upload(ws.data(), ws.size() * 2, reinterpret_cast<void**>(&dptr)))) return rc;
+        cw.whi.push_back(dptr);
+      }
     }
     if ((rc = upload(bias.data(), bias.size() * 4, reinterpret_cast<void**>(&cw.bias)))) return rc;
     convs[key] = cw;
@@ -322,6 +345,8 @@ struct Builder {
   size_t scratch_bytes = 0;                 // fp32-accurate mode: size of the plane-split scratch (from the measuring pass)
   size_t max_scratch = 0;                   //   ... largest split any conv of this plan needs
   __nv_bfloat16* scratch = nullptr;
+  size_t acc_bytes = 0, max_acc = 0;        //   ... and the fp32 partial-sum buffer of the split accumulation
+  float* accbuf = nullptr;
 
   Builder(YoloModel& m, YoloPlan& p) : M(m), P(p) {}
 
@@ -355,29 +380,47 @@ struct Builder {
       }
       const size_t need = static_cast<size_t>(P.B) * in.H * in.W * 6 * in.C * 2;
       if (need > max_scratch) max_scratch = need;
+      const size_t need_acc = static_cast<size_t>(P.B) * (stride == 2 ? in.H / 2 : in.H) * (stride == 2 ? in.W / 2 : in.W) * cw.cout * 4;
+      if (need_acc > max_acc) max_acc = need_acc;
     }
     if (bump.dry) return;
     Op op;
     op.name = key;
     if (M.precise) {
-      // fp32 slice -> six bf16 planes in the scratch, then the same tcgen05 conv over 6*Cin channels with the plane-expanded
-      // weights, fp32 output, exact SiLU
+      // fp32 slice -> six bf16 planes [lo|mid|hi|mid|hi|hi] in the scratch; then on the same tcgen05 conv kernel, all with fp32
+      // output into one dense partial-sum buffer: one GEMM per input-channel segment of the hi x hi products (hi plane at
+      // channel offset 5C), accumulated with the in-place fp32 TMA reduce-add (a round-to-nearest add at the L2), one GEMM
+      // for the five cross products (planes 0..4 against the weight planes hi|mid|lo|hi|mid); a last pass applies bias, the
+      // exact SiLU and the residual and writes the output slice.
       Op sp; sp.kind = Op::SPLIT; sp.name = key + ".split"; sp.s_in = ts(in); sp.s_out = TSlice{}; sp.s_out.p = scratch;
       P.ops.push_back(std::move(sp));
-      ConvDesc d{};
-      d.in = scratch; d.in_cs = 6 * in.C; d.in_co = 0; d.Cin = 6 * in.C;
-      d.N = P.B; d.Hin = in.H; d.Win = in.W; d.k = cw.k; d.stride = stride;
-      d.w = cw.w6; d.bias = cw.bias;
-      if (out_f32) { d.out = out_f32; d.out_cs = cw.cout; d.out_co = 0; }
-      else { d.out = out.p; d.out_cs = out.cs; d.out_co = out.co; }
-      d.out_f32 = 1;
-      d.Cout = cw.cout; d.act = act == CC_ACT_SILU ? ACT_SILU_EXACT : act;
-      if (res) { d.res = res->p; d.res_cs = res->cs; d.res_co = res->co; }
-      op.kind = Op::GEMM;
-      rc = conv_gemm_build(d, M.sms, &op.gemm);
-      if (rc) return;
-      op.gemm.flops /= 6.0;                      // algorithmic FLOPs of the conv, not of the six plane products
-      P.conv_flops += op.gemm.flops;
+      const int Ho = stride == 2 ? in.H / 2 : in.H, Wo = stride == 2 ? in.W / 2 : in.W;
+      const int nseg = static_cast<int>(cw.seg_off.size());
+      for (int g = 0; g <= nseg; ++g) {
+        ConvDesc d{};
+        d.in = scratch; d.in_cs = 6 * in.C;
+        if (g < nseg) { d.in_co = 5 * in.C + cw.seg_off[g]; d.Cin = cw.seg_c[g]; d.w = cw.whi[g]; }
+        else { d.in_co = 0; d.Cin = 5 * in.C; d.w = cw.w5; }
+        d.N = P.B; d.Hin = in.H; d.Win = in.W; d.k = cw.k; d.stride = stride;
+        d.bias = nullptr;
+        d.out = accbuf; d.out_cs = cw.cout; d.out_co = 0; d.out_f32 = 1;
+        d.Cout = cw.cout; d.act = CC_ACT_NONE;
+        if (g > 0) { d.res = accbuf; d.res_cs = cw.cout; d.res_co = 0; }
+        Op gop; gop.kind = Op::GEMM; gop.name = key + (g < nseg ? ".hi" + std::to_string(g) : ".cross");
+        rc = conv_gemm_build(d, M.sms, &gop.gemm);
+        if (rc) return;
+        if (g > 0 && gop.gemm.p.res_tma != 2) { set_error("yolo plan: conv '%s': no in-place reduce-add epilogue for the split accumulation", key.c_str()); rc = CC_ERR_STATE; return; }
+        gop.gemm.flops = g == 0 ? 2.0 * P.B * Ho * Wo * double(cw.cout) * cw.k * cw.k * cw.cin : 0.0;   // algorithmic FLOPs once
+        P.conv_flops += gop.gemm.flops;
+        P.ops.push_back(std::move(gop));
+      }
+      op.kind = Op::FINISH;
+      FinishParams& f = op.fin;
+      f = FinishParams{};
+      f.acc = accbuf; f.bias = cw.bias; f.act = act; f.npix = static_cast<long long>(P.B) * Ho * Wo; f.C = cw.cout;
+      if (out_f32) { f.out = out_f32; f.out_cs = cw.cout; f.out_co = 0; }
+      else { f.out = reinterpret_cast<float*>(out.p); f.out_cs = out.cs; f.out_co = out.co; }
+      if (res) { f.res = reinterpret_cast<const float*>(res->p); f.res_cs = res->cs; f.res_co = res->co; }
     } else if (cw.groups == 1 && tc_ok(cw.cin, cw.cout)) {
       ConvDesc d{};
       d.in = in.p; d.in_cs = in.cs; d.in_co = in.co; d.Cin = in.C;
@@ -510,7 +553,10 @@ int Builder::build() {
     }
   }
 
-  if (M.precise && !bump.dry) scratch = static_cast<__nv_bfloat16*>(dalloc(scratch_bytes));
+  if (M.precise && !bump.dry) {
+    scratch = static_cast<__nv_bfloat16*>(dalloc(scratch_bytes));
+    accbuf = static_cast<float*>(dalloc(acc_bytes));
+  }
 
   outs.assign(nl, T{});
   cbl_chunks.assign(nl, {});
@@ -728,7 +774,7 @@ static int plan_run(YoloPlan& P, const void* d_frames, float* d_out, float* d_ra
     if (ev) cudaEventRecord((*ev)[oi++], st);
     switch (op.kind) {
       case Op::GEMM:
-        if (d_trace) { GemmLaunch g = op.gemm; g.p.trace = d_trace + 3 * ti; rc = conv_gemm_launch(g, st); }
+        if (d_trace) { GemmLaunch g = op.gemm; g.p.trace = d_trace + 8 * ti; rc = conv_gemm_launch(g, st); }
         else rc = conv_gemm_launch(op.gemm, st);
         break;
       case Op::DIRECT: rc = conv_direct_launch(op.direct, st); break;
@@ -749,6 +795,7 @@ static int plan_run(YoloPlan& P, const void* d_frames, float* d_out, float* d_ra
       case Op::DECODE: { DecodeParams q = op.dec; q.raw = d_raw; rc = decode_launch(q, st); break; }
       case Op::POST: { PostParams q = op.post; q.out = d_out; rc = postprocess_launch(q, st); break; }
       case Op::SPLIT: rc = split_planes_launch(op.s_in, op.s_out.p, st); break;
+      case Op::FINISH: rc = finish_f32_launch(op.fin, st); break;
     }
     if (rc) return rc;
     ++ti;
@@ -762,7 +809,7 @@ static const char* op_kind_name(Op::Kind k) {
     case Op::GEMM: return "conv_gemm"; case Op::DIRECT: return "conv_direct"; case Op::AVGPAD: return "avgpool2_pad";
     case Op::AVGMAX: return "avgmax_pool"; case Op::MAXPOOL5: return "maxpool5"; case Op::UPSAMPLE: return "upsample2";
     case Op::CBFUSE: return "cbfuse"; case Op::LETTERBOX: return "letterbox"; case Op::STEM: return "stem"; case Op::STEM_IM2COL: return "stem_im2col"; case Op::STEM_TC: return "stem_tc";
-    case Op::DECODE: return "decode"; case Op::POST: return "postprocess"; case Op::SPLIT: return "split_planes";
+    case Op::DECODE: return "decode"; case Op::POST: return "postprocess"; case Op::SPLIT: return "split_planes"; case Op::FINISH: return "finish_f32";
   }
   return "?";
 }
@@ -883,15 +930,16 @@ static std::string plan_key(int is_f32, int B, int Hf, int Wf, int res) {
   return key;
 }
 // workspace bytes a plan of this shape addresses (measuring pass of the builder: no device work)
-static int plan_bytes(cc_yolo* h, int is_f32, int B, int Hf, int Wf, int res, size_t* bytes, size_t* scratch = nullptr) {
+static int plan_bytes(cc_yolo* h, int is_f32, int B, int Hf, int Wf, int res, size_t* bytes, size_t* scratch = nullptr, size_t* accb = nullptr) {
   YoloPlan tmp;
   tmp.B = B; tmp.Hf = Hf; tmp.Wf = Wf; tmp.res = res; tmp.is_f32 = is_f32;
   Builder dry(h->m, tmp);
   dry.bump.dry = true;
   int rc = dry.build();
   if (rc) return rc;
-  *bytes = dry.bump.off + dry.max_scratch + 4096;
+  *bytes = dry.bump.off + dry.max_scratch + dry.max_acc + 8192;
   if (scratch) *scratch = dry.max_scratch;
+  if (accb) *accb = dry.max_acc;
   return CC_OK;
 }
 static int get_plan(cc_yolo* h, int is_f32, int B, int Hf, int Wf, int res, YoloPlan** out) {
@@ -903,8 +951,8 @@ static int get_plan(cc_yolo* h, int is_f32, int B, int Hf, int Wf, int res, Yolo
     *out = it->second.get();
     return CC_OK;
   }
-  size_t bytes = 0, scratch = 0;
-  int rc = plan_bytes(h, is_f32, B, Hf, Wf, res, &bytes, &scratch);
+  size_t bytes = 0, scratch = 0, accb = 0;
+  int rc = plan_bytes(h, is_f32, B, Hf, Wf, res, &bytes, &scratch, &accb);
   if (rc) return rc;
   if ((rc = M.arena.reserve(bytes))) return rc;
   // plans built against an older workspace are stale (they are rebuilt on their next use)
@@ -915,6 +963,7 @@ static int get_plan(cc_yolo* h, int is_f32, int B, int Hf, int Wf, int res, Yolo
   Builder bld(M, *P);
   bld.bump.base = static_cast<uint8_t*>(M.arena.base);
   bld.scratch_bytes = scratch;
+  bld.acc_bytes = accb;
   rc = bld.build();
   if (rc) return rc;
   CC_REQUIRE(bld.bump.off <= M.arena.cap, "yolo plan: workspace overrun (%zu > %zu)", bld.bump.off, M.arena.cap);
@@ -1030,7 +1079,8 @@ int cc_yolo_profile(cc_yolo* h, const void* d_frames, int is_f32, int B, int Hf,
 
 /* In-situ device timeline of one forward (no events between the launches, so programmatic dependent launch overlaps
  * as in production): for every conv_gemm op, globaltimer ns of (first CTA entered, grid dependency released, last CTA
- * exited); zeros for the other ops.  host_ns: [3 * cap].  Synchronises at the end. */
+ * exited, then five stamps of CTA 0: first operands landed, all MMAs issued, first accumulator complete, last epilogue group
+ * done, exit); zeros for the other ops.  host_ns: [8 * cap].  Synchronises at the end. */
 int cc_yolo_trace(cc_yolo* h, const void* d_frames, int is_f32, int B, int Hf, int Wf, int res, float* d_out, int cap,
                   unsigned long long* host_ns, const char** kinds, const char** names, double* flops, int* n_ops, void* stream) {
   CC_REQUIRE(h && d_frames && d_out && host_ns, "cc_yolo_trace: bad argument");
@@ -1039,15 +1089,15 @@ int cc_yolo_trace(cc_yolo* h, const void* d_frames, int is_f32, int B, int Hf, i
   if (rc) return rc;
   const size_t n = P->ops.size();
   unsigned long long* d_trace = nullptr;
-  CC_CHECK_CUDA(cudaMalloc(&d_trace, n * 3 * sizeof(unsigned long long)));
+  CC_CHECK_CUDA(cudaMalloc(&d_trace, n * 8 * sizeof(unsigned long long)));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  cudaMemsetAsync(d_trace, 0, n * 3 * sizeof(unsigned long long), st);
+  cudaMemsetAsync(d_trace, 0, n * 8 * sizeof(unsigned long long), st);
   rc = plan_run(*P, d_frames, d_out, nullptr, st, nullptr, d_trace);
   if (!rc) {
     cudaError_t e = cudaStreamSynchronize(st);
     if (e == cudaSuccess) {
       const size_t m = n < static_cast<size_t>(cap) ? n : static_cast<size_t>(cap);
-      e = cudaMemcpy(host_ns, d_trace, m * 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+      e = cudaMemcpy(host_ns, d_trace, m * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
       for (size_t i = 0; i < m; ++i) {
         if (kinds) kinds[i] = op_kind_name(P->ops[i].kind);
         if (names) names[i] = P->ops[i].name.c_str();

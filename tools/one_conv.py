@@ -12,6 +12,10 @@ shapes = [  # N,H,W,Cin,Cout,k,s
     (32, 80, 80, 128, 128, 3, 1),
     (32, 160, 160, 256, 256, 1, 1),
     (32, 160, 160, 32, 32, 3, 1),
+    (32, 40, 40, 256, 256, 1, 1),
+    (32, 40, 40, 128, 128, 3, 1),
+    (32, 80, 80, 512, 512, 1, 1),
+    (32, 20, 20, 256, 256, 1, 1),
 ]
 sel = [int(a) for a in sys.argv[2:]] or range(len(shapes))
 for si in sel:
