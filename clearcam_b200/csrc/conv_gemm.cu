@@ -37,8 +37,10 @@ __device__ __forceinline__ float tanh_approx(float x) {
   return t;
 }
 
-// Epilogue activations.  The SFU (MUFU) pipe issues 16 ops/clk/SM, so an activation that needs two of them
-// (ex2 + rcp) costs 2 x 128 x BN / 16 cycles per tile — more than the MMA time of every small-K layer.
+// Epilogue activations.  tests/tools/ubench_pipes.cu on B200: tanh.approx / ex2.approx / rcp.approx all issue one warp
+// instruction per 8 cycles per scheduler (16 lanes/clk/SM), fma one per cycle, cvt.rn.bf16x2 one per 2 cycles; the packed
+// tanh.approx.bf16x2 / f16x2 take 16 cycles (no gain).  So an activation that needs two MUFU ops (ex2 + rcp) costs twice the
+// MUFU time of the tanh form, and MUFU time is what bounds a chunk of the epilogue once enough warps run it:
 //   ACT_SILU       : x*sigmoid(x) = h + h*tanh(h), h = x/2 : ONE MUFU (tanh.approx.f32, |abs err| <= 2^-11 on tanh, i.e.
 //                    <= |x| * 2.4e-4 on the result, below the bf16 rounding of the stored value for x > -2)
 //   ACT_SILU_EXACT : x / (1 + 2^(-x log2 e)) with ex2.approx + rcp.approx (two MUFU, ~1e-7 relative)
@@ -50,7 +52,7 @@ __device__ __forceinline__ float act_apply(float x) {
     return fmaf(h, tanh_approx(h), h);
   } else if (ACT == ACT_SILU_EXACT) {
     float e, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(x * -1.4426950408889634f, 126.0f)));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
     return x * r;
   } else if (ACT == ACT_GELU_TANH) {
@@ -258,10 +260,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   const uint32_t b_bytes = p.BN * row_bytes;
   const int S = p.stages;
   constexpr int es = F32 ? 4 : 2;
-  const int NG = p.n_acc;                                              // epilogue groups == TMEM accumulator slots (2 or 4)
+  const int NG = p.n_acc;                                              // TMEM accumulator slots (2 or 4)
+  const int NGRP = p.n_grp;                                            // epilogue groups (== NG, or 4 column groups sharing 2 slots)
   const int CH = p.CH;                                                 // columns per staging pass
   const uint32_t pitch = p.tma_store ? CH * es : CH * es + 16;
-  const uint32_t stg_bytes = (kTileM * pitch + 15) & ~15u;           // one staging buffer per epilogue group
+  const uint32_t stg_bytes = (kTileM * pitch + 15) & ~15u;           // one staging buffer; every epilogue group owns p.stg_nbuf of them
+  const int NBUF = p.stg_nbuf;
 
   const uint32_t a_region = p.halo ? p.halo_stages * p.halo_bytes : S * a_bytes;   // halo mode: S = B stages
   uint8_t* sA = smem;
@@ -270,7 +274,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   // resident-B mode: sB holds ALL k-blocks of the weights (loaded once); the ring then carries A only
   uint8_t* sStage = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(sB + (p.b_res ? num_kb_all : S) * b_bytes) + 1023) & ~uintptr_t(1023));
-  float* sBias = reinterpret_cast<float*>(sStage + stg_bytes * NG);
+  float* sBias = reinterpret_cast<float*>(sStage + stg_bytes * NGRP * NBUF);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + p.cout);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + S;
@@ -279,8 +283,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   uint64_t* afull_bar = bars + 2 * S + 8;       // halo mode (up to 4 stages)
   uint64_t* aempty_bar = bars + 2 * S + 12;
   uint64_t* bres_bar = bars + 2 * S + 16;       // resident-B mode
-  uint64_t* res_bar = bars + 2 * S + 17;        // residual prefetch (one per epilogue group)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 21);
+  uint64_t* res_bar = bars + 2 * S + 17;        // residual prefetch (one per staging buffer: 2 x kMaxAcc)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 25);
 
   if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[0] = globaltimer_ns();
   if (warp == 0 && lane == 0) {
@@ -295,10 +299,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
     for (int i = 0; i < kMaxAcc; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 1 << p.lgw);          // one arrival per warp of the group that owns the slot
+      mbar_init(&tempty_bar[i], p.colsplit ? (NGRP << p.lgw) : (1 << p.lgw));   // one arrival per warp that reads the slot
       mbar_init(&afull_bar[i], 1);
       mbar_init(&aempty_bar[i], 1);
-      mbar_init(&res_bar[i], 1);
+      mbar_init(&res_bar[2 * i], 1);
+      mbar_init(&res_bar[2 * i + 1], 1);
     }
     mbar_init(bres_bar, 1);
     fence_mbar_init();
@@ -397,14 +402,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     else if (p.BK == 32) CC_ISSUE(2);
     else CC_ISSUE(1);
 #undef CC_ISSUE
-  } else if (warp >= 4 && warp < 4 + (NG << p.lgw)) {
+  } else if (warp >= 4 && warp < 4 + (NGRP << p.lgw)) {
     // ===================== epilogue: NG independent groups of 4 or 8 warps.  Group g owns TMEM accumulator slot g, its own
     // staging buffer, named barrier and residual barrier, and handles every NG-th tile of this CTA, so up to NG tile
     // epilogues are in flight at once.  (One 16-warp epilogue per tile was a serial chain of ~2500 cycles — tfull wait,
     // staging-free barrier, tcgen05.ld, activation, st.shared, proxy fence, barrier, TMA store — which set the tile rate of
     // every small-K layer: 1.3-1.4 us per tile whatever the tile did, profiles/r02_issue_loop.md.)  Inside a group the
     // warp's TMEM lane quarter is warp & 3; with 8-warp groups (wide tiles) the two warps of a lane quarter split the
-    // 16-column chunks of a pass.  thread == output row in the register phase. ============
+    // 16-column chunks of a pass.  thread == output row in the register phase.
+    // Column split (p.colsplit, tiles wider than 128 columns): the in-kernel timeline showed that ONE group converting a
+    // 128 x 256 tile is a ~11000-cycle serial chain (a lone warp per scheduler issues an instruction every ~4 cycles), which is
+    // the critical path of every layer with three or fewer tiles per CTA.  There the four 4-warp groups all work on EVERY
+    // tile, group g converting columns [g BN/4, (g+1) BN/4) of it; the two accumulator slots alternate by tile. ============
     const int lgw = p.lgw;                     // log2(warps per group): 2 or 3
     const int grp = (warp - 4) >> lgw;
     const int wig = (warp - 4) & ((1 << lgw) - 1);
@@ -415,13 +424,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const int row = ew * 32 + lane;            // row of the 128-pixel tile
     const int cstep = 16 << (lgw - 2);         // column stride between the chunks one warp converts
     const uint32_t bar_id = 1 + grp;
-    uint8_t* const sbuf = sStage + grp * stg_bytes;
-    uint64_t* const rbar = &res_bar[grp];
+    uint8_t* const sbuf0 = sStage + grp * NBUF * stg_bytes;     // this group's staging buffers (pass k uses buffer k % NBUF)
+    const uint32_t sbias32 = smem_u32(sBias);
+    uint64_t* const rbar0 = &res_bar[2 * grp];
     const int TWm = (1 << p.lTW) - 1, THm = (1 << p.lTH) - 1;
-    const uint32_t t_row = tmem_base + grp * (kTmemCols / NG) + (static_cast<uint32_t>(ew * 32) << 16);
+    const bool colsplit = p.colsplit != 0;
+    const uint32_t acc_cols = kTmemCols / NG;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
+    const int gcols = colsplit ? p.BN / NGRP : p.BN;      // columns of a tile this group converts
+    const int cc_begin = colsplit ? grp * gcols : 0, cc_end = cc_begin + gcols;
     uint32_t tcount = 0;     // tiles this group has taken -> phase of its accumulator barriers
     uint32_t pass_ctr = 0;   // staging passes of this group so far
-    const int passes_per_tile = (p.BN + CH - 1) / CH;
+    const int passes_per_tile = (gcols + CH - 1) / CH;
     // TMA-store staging: rows of 128 B (SWIZZLE_128B: 16-B chunk j of row r at slot j ^ (r & 7)) or, for tiles whose
     // pass is an odd multiple of 64 B, rows of 64 B (SWIZZLE_64B: slot j ^ ((r >> 1) & 3)); sub-tiles of 128 rows follow
     // each other
@@ -432,24 +446,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     // previous store has read the buffer
     auto issue_res = [&](uint32_t k) {
       const int jg = static_cast<int>(k) / passes_per_tile;                          // k-th pass of this group
-      const int slot_k = sc.first + (grp + jg * NG) * sc.step;
+      const int slot_k = colsplit ? sc.first + jg * sc.step : sc.first + (grp + jg * NG) * sc.step;
       if (slot_k >= sc.limit) return;
       const int tile_k = slot_tile(p, sc, slot_k);
-      const int cc0k = (static_cast<int>(k) - jg * passes_per_tile) * CH;
-      const int chnk = (p.BN - cc0k) < CH ? (p.BN - cc0k) : CH;
+      const int cc0k = cc_begin + (static_cast<int>(k) - jg * passes_per_tile) * CH;
+      const int chnk = (cc_end - cc0k) < CH ? (cc_end - cc0k) : CH;
       const TileXY tk = tile_origin(p, tile_k, p.lTW);
       const int nbk = tk.nb, w0k = tk.w0, h0k = tk.h0, n0k = tk.n0;
       const int nsub = (chnk * es) >> lrow;
-      mbar_arrive_expect_tx(rbar, nsub * (kTileM << lrow));
+      const uint32_t pbk = NBUF == 2 ? (k & 1u) : 0u;
+      uint8_t* const sbufk = sbuf0 + pbk * stg_bytes;
+      uint64_t* const rbark = rbar0 + pbk;
+      mbar_arrive_expect_tx(rbark, nsub * (kTileM << lrow));
       for (int j = 0; j < nsub; ++j) {
         const int cc = nbk * p.BN + cc0k + j * (srow / es);
-        if (p.halo) tma_load_5d(sbuf + j * (kTileM << lrow), &p.tmC, rbar, cc, w0k, n0k, h0k, 0);
-        else tma_load_5d(sbuf + j * (kTileM << lrow), &p.tmC, rbar, cc, w0k, h0k, n0k, 0);
+        if (p.halo) tma_load_5d(sbufk + j * (kTileM << lrow), &p.tmC, rbark, cc, w0k, n0k, h0k, 0);
+        else tma_load_5d(sbufk + j * (kTileM << lrow), &p.tmC, rbark, cc, w0k, h0k, n0k, 0);
       }
     };
     pdl_wait();   // residual reads below depend on the previous kernel's output
     if (p.res_tma == 1 && gt == 0) issue_res(0);
-    for (int slot = sc.first + grp * sc.step; slot < sc.limit; slot += NG * sc.step, ++tcount) {
+    for (int slot = colsplit ? sc.first : sc.first + grp * sc.step; slot < sc.limit; slot += (colsplit ? 1 : NG) * sc.step, ++tcount) {
+      const uint32_t acc = colsplit ? (tcount & static_cast<uint32_t>(NG - 1)) : static_cast<uint32_t>(grp);   // accumulator slot of this tile
+      const uint32_t acc_par = colsplit ? (tcount >> (NG == 4 ? 2 : 1)) & 1u : tcount & 1u;
+      const uint32_t t_row = t_lane + acc * acc_cols;
       const TileXY tx = tile_origin(p, slot_tile(p, sc, slot), p.lTW);
       const int nb = tx.nb, w0 = tx.w0, h0 = tx.h0, n0 = tx.n0;
 
@@ -460,55 +480,62 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       const bool pvalid = (pw < p.W) && (ph < p.H) && (pn < p.N);
       const long long ppix = static_cast<long long>(pn) * p.out_ns + ph * p.W + pw;
 
-      mbar_wait(&tfull_bar[grp], tcount & 1);
+      mbar_wait(&tfull_bar[acc], acc_par);
       tc_fence_after();
       if (p.trace != nullptr && blockIdx.x == 0 && gt == 0 && grp == 0 && tcount == 0) p.trace[5] = globaltimer_ns();   // first accumulator complete
       if (p.dbg & 1) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[grp]);
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         continue;
       }
 
-      for (int cc0 = 0; cc0 < p.BN; cc0 += CH) {
-        const int chn = (p.BN - cc0) < CH ? (p.BN - cc0) : CH;  // columns in this pass (multiple of 16)
+      for (int cc0 = cc_begin; cc0 < cc_end; cc0 += CH) {
+        const int chn = (cc_end - cc0) < CH ? (cc_end - cc0) : CH;  // columns in this pass (multiple of 16)
+        const uint32_t pb = NBUF == 2 ? (pass_ctr & 1u) : 0u;      // staging buffer of this pass
+        uint8_t* const sbuf = sbuf0 + pb * stg_bytes;
+        const uint32_t sbuf32 = smem_u32(sbuf);
         if (p.res_tma == 1) {
           // the residual tile has landed in the staging buffer (which also proves the buffer was free)
-          mbar_wait(rbar, pass_ctr & 1);
+          mbar_wait(rbar0 + pb, (NBUF == 2 ? (pass_ctr >> 1) : pass_ctr) & 1);
         } else {
-          if (p.tma_store && gt == 0) tma_store_wait_read<0>();   // the previous store of this group has read the buffer
+          // the store that last read this buffer is done with it: the previous one (one buffer), or the one before it (two
+          // buffers: the previous pass's store may still be in flight — a TMA store takes ~0.3 us to issue and its smem read
+          // completes well after that, time a single buffer spent idle every pass)
+          if (p.tma_store && gt == 0) { if (NBUF == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
           named_bar_sync(bar_id, gthreads);                        // staging buffer free
         }
-        for (int c = half * 16; c < chn; c += cstep) {
-          uint32_t v[16];
-          tmem_ld16(t_row + cc0 + c, v);
+        const bool tr = p.trace != nullptr && blockIdx.x == 0 && gt == 0 && grp == 0 && tcount == 0 && cc0 == cc_begin;
+        if (tr) p.trace[8] = static_cast<unsigned long long>(clock64());   // first pass, SM cycles: staging free
+        // one 16-column chunk of this thread's row: + bias -> activation -> (+ residual) -> staging
+        auto chunk = [&](const int c, const uint32_t (&v)[16]) {
           const int gcol = nb * p.BN + cc0 + c;  // global output channel of v[0]
-          float bia[16];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 b4 = *reinterpret_cast<const float4*>(sBias + gcol + 4 * j);
-            bia[4 * j] = b4.x; bia[4 * j + 1] = b4.y; bia[4 * j + 2] = b4.z; bia[4 * j + 3] = b4.w;
-          }
-          tmem_ld_wait();
           float f[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = act_apply<ACT>(__uint_as_float(v[j]) + bia[j]);
+          for (int j = 0; j < 4; ++j) {
+            const float4 b4 = lds_f4(sbias32 + (gcol + 4 * j) * 4);
+            f[4 * j] = act_apply<ACT>(__uint_as_float(v[4 * j]) + b4.x);
+            f[4 * j + 1] = act_apply<ACT>(__uint_as_float(v[4 * j + 1]) + b4.y);
+            f[4 * j + 2] = act_apply<ACT>(__uint_as_float(v[4 * j + 2]) + b4.z);
+            f[4 * j + 3] = act_apply<ACT>(__uint_as_float(v[4 * j + 3]) + b4.w);
+          }
           if (p.res_tma == 2) {
             // nothing to read: the TMA reduce-add store adds the residual in place
           } else if (p.res_tma == 1) {
             const uint32_t boff = c * es;
-            const uint8_t* sub = sbuf + (boff >> lrow) * (kTileM << lrow) + (row << lrow);
+            const uint32_t sub = sbuf32 + (boff >> lrow) * (kTileM << lrow) + (row << lrow);
             const uint32_t ch0 = (boff & (srow - 1)) >> 4;
             if (F32) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const float4 r = *reinterpret_cast<const float4*>(sub + (((ch0 + j) ^ swz) << 4));
+                const uint4 ru = lds_u4(sub + (((ch0 + j) ^ swz) << 4));
+                const float4 r = make_float4(__uint_as_float(ru.x), __uint_as_float(ru.y), __uint_as_float(ru.z), __uint_as_float(ru.w));
                 f[4 * j + 0] += r.x; f[4 * j + 1] += r.y; f[4 * j + 2] += r.z; f[4 * j + 3] += r.w;
               }
             } else {
 #pragma unroll
               for (int j = 0; j < 2; ++j) {
-                const uint4 r = *reinterpret_cast<const uint4*>(sub + (((ch0 + j) ^ swz) << 4));
+                const uint4 r = lds_u4(sub + (((ch0 + j) ^ swz) << 4));
                 const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -544,19 +571,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           }
           if (p.tma_store) {
             const uint32_t boff = c * es;                       // byte offset of this 16-column group in the pass row
-            uint8_t* sub = sbuf + (boff >> lrow) * (kTileM << lrow) + (row << lrow);
+            const uint32_t sub = sbuf32 + (boff >> lrow) * (kTileM << lrow) + (row << lrow);
             const uint32_t ch0 = (boff & (srow - 1)) >> 4;
             if (F32) {
 #pragma unroll
               for (int j = 0; j < 4; ++j)
-                *reinterpret_cast<float4*>(sub + (((ch0 + j) ^ swz) << 4)) =
-                    make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                sts_u4(sub + (((ch0 + j) ^ swz) << 4), __float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]),
+                       __float_as_uint(f[4 * j + 3]));
             } else {
 #pragma unroll
               for (int j = 0; j < 2; ++j)
-                *reinterpret_cast<uint4*>(sub + (((ch0 + j) ^ swz) << 4)) =
-                    make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                               pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+                sts_u4(sub + (((ch0 + j) ^ swz) << 4), pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                       pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
             }
           } else {
             uint8_t* dst = sbuf + row * pitch + c * es;
@@ -572,14 +598,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                                pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
             }
           }
+        };
+        // two chunks' TMEM loads go out before the one tcgen05.wait::ld (the in-kernel timeline puts the TMEM read at ~150 cycles;
+        // the conversion of a chunk at 450-950 cycles depending on how many warps share the scheduler's MUFU pipe)
+        for (int c = half * 16; c < chn; c += 2 * cstep) {
+          const bool two = c + cstep < chn;                        // warp-uniform
+          uint32_t va[16], vb[16];
+          tmem_ld16(t_row + cc0 + c, va);
+          if (two) tmem_ld16(t_row + cc0 + c + cstep, vb);
+          tmem_ld_wait();
+          if (tr && c == half * 16) p.trace[9] = static_cast<unsigned long long>(clock64());     // ... TMEM loads returned
+          chunk(c, va);
+          if (tr && c == half * 16) p.trace[10] = static_cast<unsigned long long>(clock64());    // ... first chunk staged
+          if (two) chunk(c + cstep, vb);
         }
-        if (cc0 + CH >= p.BN) {
+        if (cc0 + CH >= cc_end) {
           // all TMEM reads of this accumulator done -> hand it back to the MMA warp.  ONE arrival per warp: hundreds of
           // threads arriving on the same mbarrier serialise in the LSU (CC_DBG bisection, profiles/r02)
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[grp]);
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
+        if (tr) p.trace[11] = static_cast<unsigned long long>(clock64());  // ... all of this thread's chunks staged
         if (p.tma_store) {
           fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the TMA (async proxy)
           named_bar_sync(bar_id, gthreads);  // staging filled
@@ -596,7 +636,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             }
             tma_store_commit();
             if (p.res_tma == 1) {
-              tma_store_wait_read<0>();      // the buffer is free again once the store has read it
+              // the next pass's buffer is free once its last store has read it (this one with a single buffer, the
+              // previous one with two)
+              if (NBUF == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
               issue_res(pass_ctr + 1);
             }
           }
@@ -821,9 +863,19 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
   // 4 stages) the next level halves it: 2 groups of 4 warps (BN <= 128) / 64-column passes (BN = 256).
   static const int nacc_env = getenv("CC_NACC") ? atoi(getenv("CC_NACC")) : 4;
   int level = (BN <= 128 && nacc_env == 2) ? 1 : 0;
+  // two staging buffers per epilogue group where the operand pipeline keeps its depth (>= 3 halo buffers / >= 4 stages): a pass
+  // then never waits for the previous pass's TMA store
+  static const int nbuf_env = getenv("CC_STG_NBUF") ? atoi(getenv("CC_STG_NBUF")) : 2;
+  int nbuf = nbuf_env == 1 ? 1 : 2;
+  static const int colsplit_env = getenv("CC_COLSPLIT") ? atoi(getenv("CC_COLSPLIT")) : 1;
+  int cs = colsplit_env;      // column split wanted (dropped again below when its staging squeezes the operand pipeline)
 budget_again:
-  if (BN > 128) { p.n_acc = 2; p.lgw = 3; }
-  else { p.n_acc = level == 0 ? 4 : 2; p.lgw = 2; }
+  p.stg_nbuf = nbuf;
+  // column split for wide tiles: four 4-warp groups each convert a quarter of every tile's columns (see the kernel)
+  p.colsplit = (cs && BN > 128 && (BN / 4) % (d.out_f32 ? 32 : 64) == 0) ? 1 : 0;
+  if (p.colsplit) { p.n_acc = 2; p.n_grp = 4; p.lgw = 2; }
+  else if (BN > 128) { p.n_acc = 2; p.n_grp = 2; p.lgw = 3; }
+  else { p.n_acc = level == 0 ? 4 : 2; p.n_grp = p.n_acc; p.lgw = 2; }
   int CH = (p.lgw == 2 || level >= 1) ? (d.out_f32 ? 32 : 64) : (d.out_f32 ? 64 : 128);
   if (CH > BN) CH = BN;
   p.CH = CH;
@@ -860,9 +912,9 @@ budget_again:
   p.res_tma = (restma_env && p.tma_store && d.res != nullptr && d.res == d.out && d.res_cs == d.out_cs && d.res_co == d.out_co) ? 1 : 0;
   if (p.res_tma && d.out_f32 && restma_env >= 1 && restma_env != 3) p.res_tma = 2;   // fp32: reduce-add store (CC_RES_TMA=3 forces the prefetch variant)
   const int pitch = p.tma_store ? CH * es : CH * es + 16;
-  const int staging = ((kTileM * pitch + 15) & ~15) * p.n_acc;
+  const int staging = ((kTileM * pitch + 15) & ~15) * p.n_grp * nbuf;
   const int stage_bytes = kTileM * p.BK * 2 + BN * p.BK * 2;
-  const int fixed = 1024 /*alignment slack of the smem base*/ + staging + d.Cout * 4 /*bias*/ + 304 /*barriers + TMEM slot*/;
+  const int fixed = 1024 /*alignment slack of the smem base*/ + staging + d.Cout * 4 /*bias*/ + 336 /*barriers + TMEM slot*/;
   // the staging area starts at the next 1024-B boundary after the operand rings (a no-op unless a weight tile is an odd
   // multiple of 512 B)
   auto stage_pad = [](int operand_bytes) { return (1024 - operand_bytes % 1024) % 1024; };
@@ -893,7 +945,10 @@ budget_again:
     // budget: staging (already in `fixed`), then weights (resident, or a ring of >= 3 taps), then as many halo
     // buffers as fit (2..4): a halo chunk is only 9 taps of MMA work, so 2 buffers cannot hide the TMA latency
     int avail = kMaxSmem - fixed;
-    if (p.b_res && avail - bres_bytes < 2 * p.halo_bytes) p.b_res = 0;
+    if (p.b_res && avail - bres_bytes < 2 * p.halo_bytes) {
+      if (nbuf == 2) { nbuf = 1; goto budget_again; }   // resident weights beat the second staging buffer
+      p.b_res = 0;
+    }
     int wbytes;
     if (p.b_res) { wbytes = bres_bytes; S = 2; }
     else {
@@ -904,6 +959,8 @@ budget_again:
     int hs = (avail - wbytes) / p.halo_bytes;
     if (hs > 4) hs = 4;
     if (hst_env >= 2 && hst_env <= 4 && hst_env < hs) hs = hst_env;
+    if (hs < 3 && nbuf == 2) { nbuf = 1; goto budget_again; }
+    if (hs < 3 && p.colsplit) { cs = 0; nbuf = nbuf_env == 1 ? 1 : 2; goto budget_again; }   // K-heavy 3x3 tiles: the mainloop matters more
     if (hs < 3 && level == 0) {   // the staging squeezes the halo ring: halve it (an MMA-bound layer does not need more)
       level = 1;
       goto budget_again;
@@ -920,11 +977,16 @@ budget_again:
     if (S > 8) S = 8;
     if (fixed + bres_bytes + S * a_bytes + stage_pad(bres_bytes + S * a_bytes) > kMaxSmem) --S;
     L->smem_bytes = fixed + bres_bytes + S * a_bytes + stage_pad(bres_bytes + S * a_bytes);
+  } else if (p.b_res && nbuf == 2) {   // keep the weights resident rather than the second staging buffer
+    nbuf = 1;
+    goto budget_again;
   } else {
     p.b_res = 0;
     S = (kMaxSmem - fixed) / stage_bytes;
     if (S > 8) S = 8;
-    if (S < 4 && level == 0) {
+    if (S < 4 && nbuf == 2) { nbuf = 1; goto budget_again; }
+    if (S < 3 && p.colsplit) { cs = 0; nbuf = nbuf_env == 1 ? 1 : 2; goto budget_again; }
+    if (S < 4 && level == 0 && !p.colsplit) {
       level = 1;
       goto budget_again;
     }

@@ -58,6 +58,8 @@ struct GemmParams {
   // every weight tile and multicasts it to both (halves the weight traffic L2 -> SM of the wide GEMMs, which are bound by it)
   int32_t pair, n_super;              // enabled / number of (M-tile pair, N block) super tiles
   int32_t CH;                         // output columns per staging pass of one epilogue group
+  int32_t stg_nbuf;                   // staging buffers per epilogue group (1 or 2)
+  int32_t n_grp, colsplit;            // epilogue groups; 1: every group converts its share of the columns of EVERY tile
   unsigned long long* trace;          // optional device timeline slots [8] (globaltimer ns): first CTA entry, dependency released, last CTA exit,
                                       // and of CTA 0: first operands landed, all MMAs issued, first accumulator complete, last epilogue done, exit
 };

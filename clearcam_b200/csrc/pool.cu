@@ -120,56 +120,11 @@ __global__ void avgpool2_pad_kernel(TSlice in, TSlice out) {
   }
   Vec8<E>::st(at_w<E>(out, q.n, q.h, q.w, q.c), r);
 }
-// Tiled variant for slices whose width is a multiple of 64 channels: a block owns an 8 x 8 pixel x 64-channel output tile and
-// stages its 9 x 9 input window in shared memory once, so every input vector crosses the L2 -> SM fabric ~1.3 times instead
-// of 4 (the row-structured kernel above re-reads each input row from the L2 for the output row above it and relies on the
-// L1 for the horizontal neighbour; it ran at the L2's bandwidth, not HBM's).  Same arithmetic, same results.
-template <typename E>
-__global__ void __launch_bounds__(256) avgpool2_pad_tiled_kernel(TSlice in, TSlice out, int cblocks) {
-  __shared__ __align__(16) E tile[9 * 9 * 64];
-  const int cb = blockIdx.x % cblocks, tx = blockIdx.x / cblocks;
-  const int x0 = tx * 8, y0 = blockIdx.y * 8, n = blockIdx.z, c0 = cb * 64;
-  for (int i = threadIdx.x; i < 81 * 8; i += 256) {
-    const int v = i & 7, pxl = i >> 3, r = pxl / 9, c = pxl - r * 9;
-    const int y = min(y0 + r, in.H - 1), x = min(x0 + c, in.W - 1);      // clamped: never used past the edge
-    *reinterpret_cast<typename Vec8<E>::raw_t*>(tile + pxl * 64 + v * 8) = Vec8<E>::ld_raw(at<E>(in, n, y, x, c0 + v * 8));
-  }
-  __syncthreads();
-  const int v = threadIdx.x & 7, px = threadIdx.x >> 3, lx = px & 7;
-#pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const int ly = (px >> 3) + 4 * k;
-    const int oy = y0 + ly, ox = x0 + lx;
-    if (oy >= out.H || ox >= out.W) continue;
-    bf8 r;
-    if (oy < in.H - 1 && ox < in.W - 1) {
-      const E* p0 = tile + (ly * 9 + lx) * 64 + v * 8;
-      const bf8 a = Vec8<E>::unpack(*reinterpret_cast<const typename Vec8<E>::raw_t*>(p0)),
-                b = Vec8<E>::unpack(*reinterpret_cast<const typename Vec8<E>::raw_t*>(p0 + 64)),
-                d = Vec8<E>::unpack(*reinterpret_cast<const typename Vec8<E>::raw_t*>(p0 + 9 * 64)),
-                e = Vec8<E>::unpack(*reinterpret_cast<const typename Vec8<E>::raw_t*>(p0 + 10 * 64));
-#pragma unroll
-      for (int i = 0; i < 8; ++i) r.v[i] = ((a.v[i] + b.v[i]) + (d.v[i] + e.v[i])) * 0.25f;
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) r.v[i] = 0.f;
-    }
-    Vec8<E>::st(at_w<E>(out, n, oy, ox, c0 + v * 8), r);
-  }
-}
 int avgpool2_pad_launch(const TSlice& in, const TSlice& out, cudaStream_t s) {
   CC_REQUIRE(in.C % 8 == 0 && in.co % 8 == 0 && in.cs % 8 == 0 && out.co % 8 == 0 && out.cs % 8 == 0 && in.C == out.C &&
                  in.H == out.H && in.W == out.W, "avgpool2_pad: bad slices");
   CC_REQUIRE(out.H <= 65535 && out.N <= 65535, "avgpool2_pad: tensor too large for the row grid");
   CC_REQUIRE(in.f32 == out.f32, "avgpool2_pad: mixed element types");
-  static const int tiled_env = getenv("CC_POOL_TILED") ? atoi(getenv("CC_POOL_TILED")) : 0;
-  if (tiled_env && in.C % 64 == 0 && !in.f32) {
-    const int cblocks = in.C / 64;
-    const dim3 grid(((out.W + 7) / 8) * cblocks, (out.H + 7) / 8, out.N);
-    avgpool2_pad_tiled_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(in, out, cblocks);
-    CC_CHECK_CUDA(cudaGetLastError());
-    return CC_OK;
-  }
   const int t = row_threads(out);
   CC_LAUNCH_E(avgpool2_pad_kernel, in.f32, row_grid(out, t), t, s, in, out);
   CC_CHECK_CUDA(cudaGetLastError());
@@ -228,8 +183,10 @@ __global__ void __launch_bounds__(256, 2) avgmax_pool_kernel(TSlice in, TSlice o
           if (cv[c]) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float av = Vec8<E>::round_store((hp[c][i] + h[c][i]) * 0.25f);   // the reference max-pools the STORED avg map
-              m[i] = fmaxf(m[i], av);
+              // the reference max-pools the STORED (rounded) avg map; rounding to the storage type is monotonic, so
+              // max(round(a_i)) == round(max(a_i)) and the one rounding happens in the final store (nine bf16 conversions
+              // per element kept this kernel bound by the conversion unit: ncu sm__inst_executed_pipe_xu 37 %)
+              m[i] = fmaxf(m[i], (hp[c][i] + h[c][i]) * 0.25f);
             }
           }
         }
@@ -245,89 +202,12 @@ __global__ void __launch_bounds__(256, 2) avgmax_pool_kernel(TSlice in, TSlice o
   for (int i = 0; i < 8; ++i) o.v[i] = m[i];
   Vec8<E>::st(at_w<E>(out, q.n, q.h, q.w, q.c), o);
 }
-// Tiled variant (slice width a multiple of 64 channels): a block owns an 8 wide x 4 high output tile x 64 channels and stages
-// its 18 x 10 input window in shared memory once (each input vector is needed by up to four outputs; the kernel above
-// fetched all of them through the L2, 4x the tensor, and ran at the L2's bandwidth).  Same arithmetic, same results.
-template <typename E>
-__global__ void __launch_bounds__(256) avgmax_pool_tiled_kernel(TSlice in, TSlice out, int cblocks) {
-  __shared__ __align__(16) E tile[10 * 18 * 64];
-  const int cb = blockIdx.x % cblocks, tx = blockIdx.x / cblocks;
-  const int ox0 = tx * 8, oy0 = blockIdx.y * 4, n = blockIdx.z, c0 = cb * 64;
-  const int iy0 = 2 * oy0 - 1, ix0 = 2 * ox0 - 1;
-  for (int i = threadIdx.x; i < 180 * 8; i += 256) {
-    const int v = i & 7, pxl = i >> 3, r = pxl / 18, c = pxl - r * 18;
-    const int y = min(max(iy0 + r, 0), in.H - 1), x = min(max(ix0 + c, 0), in.W - 1);   // clamped: masked below when outside
-    *reinterpret_cast<typename Vec8<E>::raw_t*>(tile + pxl * 64 + v * 8) = Vec8<E>::ld_raw(at<E>(in, n, y, x, c0 + v * 8));
-  }
-  __syncthreads();
-  const int v = threadIdx.x & 7, px = threadIdx.x >> 3, lx = px & 7, ly = px >> 3;
-  const int oy = oy0 + ly, ox = ox0 + lx;
-  if (oy >= out.H || ox >= out.W) return;
-  const int Ha = in.H - 1, Wa = in.W - 1;
-  const int y0 = 2 * oy - 1, x0 = 2 * ox - 1;
-  bool cv[3];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) cv[c] = (x0 + c >= 0) && (x0 + c < Wa);
-  float m[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
-  float hp[3][8];                    // row-pair sums (a+b) of the previous input row
-  const E* base = tile + ((2 * ly) * 18 + 2 * lx) * 64 + v * 8;
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    float h[3][8];
-    {
-      const E* rp = base + r * 18 * 64;
-      const bf8 v0 = Vec8<E>::unpack(*reinterpret_cast<const typename Vec8<E>::raw_t*>(rp)),
-                v1 = Vec8<E>::unpack(*reinterpret_cast<const typename Vec8<E>::raw_t*>(rp + 64)),
-                v2 = Vec8<E>::unpack(*reinterpret_cast<const typename Vec8<E>::raw_t*>(rp + 128)),
-                v3 = Vec8<E>::unpack(*reinterpret_cast<const typename Vec8<E>::raw_t*>(rp + 192));
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        h[0][i] = v0.v[i] + v1.v[i];
-        h[1][i] = v1.v[i] + v2.v[i];
-        h[2][i] = v2.v[i] + v3.v[i];
-      }
-    }
-    if (r >= 1) {
-      const int ya = y0 + r - 1;     // avg row = input rows (ya, ya+1)
-      if (ya >= 0 && ya < Ha) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          if (cv[c]) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float av = Vec8<E>::round_store((hp[c][i] + h[c][i]) * 0.25f);   // the reference max-pools the STORED avg map
-              m[i] = fmaxf(m[i], av);
-            }
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) hp[c][i] = h[c][i];
-  }
-  bf8 o;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) o.v[i] = m[i];
-  Vec8<E>::st(at_w<E>(out, n, oy, ox, c0 + v * 8), o);
-}
 int avgmax_pool_launch(const TSlice& in, const TSlice& out, cudaStream_t s) {
   CC_REQUIRE(in.C % 8 == 0 && in.co % 8 == 0 && in.cs % 8 == 0 && out.co % 8 == 0 && out.cs % 8 == 0 && in.C == out.C,
              "avgmax_pool: bad slices");
   CC_REQUIRE(out.H == (in.H - 1 + 2 - 3) / 2 + 1 && out.W == (in.W - 1 + 2 - 3) / 2 + 1, "avgmax_pool: bad output extent");
   CC_REQUIRE(out.H <= 65535 && out.N <= 65535, "avgmax_pool: tensor too large for the row grid");
   CC_REQUIRE(in.f32 == out.f32, "avgmax_pool: mixed element types");
-  static const int tiled_env = getenv("CC_POOL_TILED") ? atoi(getenv("CC_POOL_TILED")) : 0;
-  if (tiled_env && in.C % 64 == 0 && !in.f32) {
-    const int cblocks = in.C / 64;
-    const dim3 grid(((out.W + 7) / 8) * cblocks, (out.H + 3) / 4, out.N);
-    avgmax_pool_tiled_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(in, out, cblocks);
-    CC_CHECK_CUDA(cudaGetLastError());
-    return CC_OK;
-  }
   const int t = row_threads(out);
   CC_LAUNCH_E(avgmax_pool_kernel, in.f32, row_grid(out, t), t, s, in, out);
   CC_CHECK_CUDA(cudaGetLastError());

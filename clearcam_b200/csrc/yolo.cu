@@ -774,7 +774,7 @@ static int plan_run(YoloPlan& P, const void* d_frames, float* d_out, float* d_ra
     if (ev) cudaEventRecord((*ev)[oi++], st);
     switch (op.kind) {
       case Op::GEMM:
-        if (d_trace) { GemmLaunch g = op.gemm; g.p.trace = d_trace + 8 * ti; rc = conv_gemm_launch(g, st); }
+        if (d_trace) { GemmLaunch g = op.gemm; g.p.trace = d_trace + 12 * ti; rc = conv_gemm_launch(g, st); }
         else rc = conv_gemm_launch(op.gemm, st);
         break;
       case Op::DIRECT: rc = conv_direct_launch(op.direct, st); break;
@@ -1080,7 +1080,7 @@ int cc_yolo_profile(cc_yolo* h, const void* d_frames, int is_f32, int B, int Hf,
 /* In-situ device timeline of one forward (no events between the launches, so programmatic dependent launch overlaps
  * as in production): for every conv_gemm op, globaltimer ns of (first CTA entered, grid dependency released, last CTA
  * exited, then five stamps of CTA 0: first operands landed, all MMAs issued, first accumulator complete, last epilogue group
- * done, exit); zeros for the other ops.  host_ns: [8 * cap].  Synchronises at the end. */
+ * done, exit); zeros for the other ops.  host_ns: [12 * cap].  Synchronises at the end. */
 int cc_yolo_trace(cc_yolo* h, const void* d_frames, int is_f32, int B, int Hf, int Wf, int res, float* d_out, int cap,
                   unsigned long long* host_ns, const char** kinds, const char** names, double* flops, int* n_ops, void* stream) {
   CC_REQUIRE(h && d_frames && d_out && host_ns, "cc_yolo_trace: bad argument");
@@ -1089,15 +1089,15 @@ int cc_yolo_trace(cc_yolo* h, const void* d_frames, int is_f32, int B, int Hf, i
   if (rc) return rc;
   const size_t n = P->ops.size();
   unsigned long long* d_trace = nullptr;
-  CC_CHECK_CUDA(cudaMalloc(&d_trace, n * 8 * sizeof(unsigned long long)));
+  CC_CHECK_CUDA(cudaMalloc(&d_trace, n * 12 * sizeof(unsigned long long)));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  cudaMemsetAsync(d_trace, 0, n * 8 * sizeof(unsigned long long), st);
+  cudaMemsetAsync(d_trace, 0, n * 12 * sizeof(unsigned long long), st);
   rc = plan_run(*P, d_frames, d_out, nullptr, st, nullptr, d_trace);
   if (!rc) {
     cudaError_t e = cudaStreamSynchronize(st);
     if (e == cudaSuccess) {
       const size_t m = n < static_cast<size_t>(cap) ? n : static_cast<size_t>(cap);
-      e = cudaMemcpy(host_ns, d_trace, m * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+      e = cudaMemcpy(host_ns, d_trace, m * 12 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
       for (size_t i = 0; i < m; ++i) {
         if (kinds) kinds[i] = op_kind_name(P->ops[i].kind);
         if (names) names[i] = P->ops[i].name.c_str();

@@ -317,18 +317,19 @@ class YOLOv9:
         B, Hf, Wf, _ = t.shape
         out = torch.empty(B, 300, 6, device="cuda", dtype=torch.float32)
         cap = 1024
-        ns = (ctypes.c_ulonglong * (8 * cap))()
+        ns = (ctypes.c_ulonglong * (12 * cap))()
         fl = (ctypes.c_double * cap)()
         kinds = (ctypes.c_char_p * cap)()
         names = (ctypes.c_char_p * cap)()
         n = ctypes.c_int()
         check(lib().cc_yolo_trace(self._h, ptr(t), 1 if t.dtype == torch.float32 else 0, B, Hf, Wf, self.res, ptr(out), cap,
                                   ns, kinds, names, fl, ctypes.byref(n), stream_ptr()), "cc_yolo_trace")
-        t0 = min(ns[8 * i] for i in range(n.value) if ns[8 * i])
+        t0 = min(ns[12 * i] for i in range(n.value) if ns[12 * i])
         rel = lambda v: (v - t0) if v else 0
-        return [{"kind": kinds[i].decode(), "name": names[i].decode(), "flops": fl[i], "t_in": rel(ns[8 * i]),
-                 "t_dep": rel(ns[8 * i + 1]), "t_out": rel(ns[8 * i + 2]),
-                 "cta0": [rel(ns[8 * i + j]) for j in range(3, 8)]} for i in range(n.value)]
+        return [{"kind": kinds[i].decode(), "name": names[i].decode(), "flops": fl[i], "t_in": rel(ns[12 * i]),
+                 "t_dep": rel(ns[12 * i + 1]), "t_out": rel(ns[12 * i + 2]),
+                 "cta0": [rel(ns[12 * i + j]) for j in range(3, 8)],
+                 "pass_cycles": [int(ns[12 * i + j]) - int(ns[12 * i + 8]) for j in range(9, 12)]} for i in range(n.value)]
 
     def layer_output(self, layer: int, B, Hf, Wf, is_f32=False):
         """Parity tap: output of graph layer `layer` of the last forward with this shape, as fp32 (B,C,H,W), or None."""

@@ -99,9 +99,9 @@ int cc_yolo_profile(cc_yolo* h, const void* d_frames, int is_f32, int B, int Hf,
                     float* ms, double* flops, double* bytes, const char** kinds, const char** names, int* n_ops, void* stream);
 
 /* measurement: in-situ device timeline of one forward, no events between the launches (so programmatic dependent launch
- * overlaps exactly as in production).  For op i, host_ns[8i..8i+7] = globaltimer ns of (first CTA entered, grid
+ * overlaps exactly as in production).  For op i, host_ns[12i..12i+11] = globaltimer ns of (first CTA entered, grid
  * dependency released, last CTA exited; then of CTA 0: first operands landed, all MMAs issued, first accumulator complete,
- * last epilogue group done, exit) for the tensor-core conv launches, zeros for the other kernels.  Synchronises. */
+ * last epilogue group done, exit; then four stamps inside the first staging pass of its first tile) for the tensor-core conv launches, zeros for the other kernels.  Synchronises. */
 int cc_yolo_trace(cc_yolo* h, const void* d_frames, int is_f32, int B, int Hf, int Wf, int res, float* d_out, int cap,
                   unsigned long long* host_ns, const char** kinds, const char** names, double* flops, int* n_ops, void* stream);
 

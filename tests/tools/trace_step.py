@@ -25,7 +25,7 @@ for _ in range(5):
         best = (span, tr)
 span, tr = best
 print(f"span first conv entry -> last conv exit: {span/1e6:.3f} ms (B={B})")
-print(f"{'#':>3} {'kind':12s} {'name':34s} {'t_in_us':>9s} {'t_dep_us':>9s} {'t_out_us':>9s} {'work_us':>8s} {'gap_us':>7s} {'ideal_us':>8s} | CTA 0, us after t_dep: operands landed, MMAs issued, first acc done, epilogue done, exit")
+print(f"{'#':>3} {'kind':12s} {'name':34s} {'t_in_us':>9s} {'t_dep_us':>9s} {'t_out_us':>9s} {'work_us':>8s} {'gap_us':>7s} {'ideal_us':>8s} | CTA 0, us after t_dep: operands landed, MMAs issued, first acc done, epilogue done, exit) | first staging pass, SM cycles after 'staging free': TMEM loads returned, first chunk staged, all chunks staged")
 prev_out = 0
 tw = tg = 0.0
 nonconv = []
@@ -39,6 +39,6 @@ for i, r in enumerate(tr):
     tw += work
     tg += gap
     c0 = " ".join(f"{(v - r['t_dep'])/1e3:6.2f}" if v else "     -" for v in r["cta0"])     # CTA 0 stamps relative to t_dep
-    print(f"{i:3d} {r['kind']:12s} {r['name']:34s} {r['t_in']/1e3:9.2f} {r['t_dep']/1e3:9.2f} {r['t_out']/1e3:9.2f} {work:8.2f} {gap:7.2f} {r['flops']/1443e6:8.2f} | {c0}")
+    print(f"{i:3d} {r['kind']:12s} {r['name']:34s} {r['t_in']/1e3:9.2f} {r['t_dep']/1e3:9.2f} {r['t_out']/1e3:9.2f} {work:8.2f} {gap:7.2f} {r['flops']/1443e6:8.2f} | {c0} | {r['pass_cycles']}")
     prev_out = r["t_out"]
 print(f"sum of conv work {tw/1e3:.3f} ms, sum of gaps (boundaries + non-conv kernels) {tg/1e3:.3f} ms")
