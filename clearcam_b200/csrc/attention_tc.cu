@@ -386,13 +386,17 @@ static int attention_group(int B, int L) {
 static int attention_lk(int B, int L) { return (attention_group(B, L) * L + 63) / 64 * 64; }
 
 bool attention_tc_supported(int L) {
-  // CC_ATTN_TC: 0 = never (legacy mma.sync kernel), 1 (default) / 2 = wherever it fits.  Read when a plan is built, so tests
-  // can force either path.  (Round 1 kept the 50- and 77-token sequences on mma.sync: one (image, head) per CTA left most of
-  // the 128-row block empty; packed groups removed that.)
+  // CC_ATTN_TC: 0 = never (mma.sync kernel of vit.cu), 1 (default) = by measured speed, 2 = wherever it fits.  Read when a plan
+  // is built, so tests can force either path.  Measured on B200 (bench.py --workload clip, per 12- or 24-layer forward, B = 256):
+  // ViT-L/14 image tower (257 tokens) 13.4 ms here vs 17.0 ms on the mma.sync kernel; ViT-B/32 image tower (50 tokens, packed
+  // five images per CTA) 0.82 ms here vs 0.44 ms there, text tower (77 tokens) 12 % slower here: the short sequences are bound
+  // by this kernel's serial per-CTA chain (loads -> S -> softmax -> PV with one CTA per SM), which the mma.sync kernel hides with
+  // several CTAs per SM.  So by default the tcgen05 kernel takes the sequences longer than one 128-row block.
   const char* e = getenv("CC_ATTN_TC");
   const int mode = e ? atoi(e) : 1;
   const int Lk = (L + 63) / 64 * 64;
   if (mode == 0 || Lk > kMaxLk) return false;
+  if (mode == 1) return L > 128;
   return true;
 }
 size_t attention_tc_workspace_bytes(int B, int L, int H) {

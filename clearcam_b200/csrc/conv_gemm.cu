@@ -111,7 +111,7 @@ __device__ __forceinline__ int lane_id() { return static_cast<int>(threadIdx.x &
 // ~60 dependent instructions (~300 cycles: R2UR moves, constant loads, reconvergence) — more than the tensor time of a
 // k-block at BN <= 128 — so the loops below issue as much as they can per block: with resident weights all nine taps of
 // a halo chunk (plus both commits) go out under ONE elect, otherwise one block per k-block with the commits folded in.
-// (CC_DBG bisection + ncu source view, profiles/r02_issue_loop.md)
+// (CC_DBG bisection + ncu source view, profiles/round1/r02_issue_loop.md)
 template <int KPB>
 __device__ __forceinline__ void mma_kblock(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   umma_f16(d_tmem, adesc, bdesc, idesc, accumulate);
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     // staging buffer, named barrier and residual barrier, and handles every NG-th tile of this CTA, so up to NG tile
     // epilogues are in flight at once.  (One 16-warp epilogue per tile was a serial chain of ~2500 cycles — tfull wait,
     // staging-free barrier, tcgen05.ld, activation, st.shared, proxy fence, barrier, TMA store — which set the tile rate of
-    // every small-K layer: 1.3-1.4 us per tile whatever the tile did, profiles/r02_issue_loop.md.)  Inside a group the
+    // every small-K layer: 1.3-1.4 us per tile whatever the tile did, profiles/round1/r02_issue_loop.md.)  Inside a group the
     // warp's TMEM lane quarter is warp & 3; with 8-warp groups (wide tiles) the two warps of a lane quarter split the
     // 16-column chunks of a pass.  thread == output row in the register phase.
     // Column split (p.colsplit, tiles wider than 128 columns): the in-kernel timeline showed that ONE group converting a
@@ -614,7 +614,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         }
         if (cc0 + CH >= cc_end) {
           // all TMEM reads of this accumulator done -> hand it back to the MMA warp.  ONE arrival per warp: hundreds of
-          // threads arriving on the same mbarrier serialise in the LSU (CC_DBG bisection, profiles/r02)
+          // threads arriving on the same mbarrier serialise in the LSU (CC_DBG bisection, profiles/round1/)
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[acc]);

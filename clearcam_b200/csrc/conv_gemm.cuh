@@ -48,7 +48,7 @@ struct GemmParams {
   int32_t b_res;                      // weights of the (single) N block stay resident in smem for the whole kernel
   int32_t res_tma;                    // in-place residual is prefetched into the staging buffer by TMA (through tmC)
   // tile index -> (n block, w, h, n) without integer division: q = (umulhi(mul, x) + x) >> shift (per-tile index
-  // math was ~140 of the ~260 instructions every epilogue warp spends per tile; ncu profiles/r02)
+  // math was ~140 of the ~260 instructions every epilogue warp spends per tile; ncu, profiles/round1/)
   uint32_t fd_nb[2], fd_tw[2], fd_th[2], fd_twh[2];
   int32_t stg_lrow;                   // log2 of the staging / TMA-store row: 7 (SWIZZLE_128B) or 6 (SWIZZLE_64B, narrow tiles)
   int32_t dbg;                        // CC_DBG bisection switches (never set in production): 1 no epilogue work, 4 no A loads

@@ -228,6 +228,34 @@ def test_multi_camera_batch_matches_single_frame_calls():
             assert [int(t_.track_id) for t_ in exp] == [int(t_.track_id) for t_ in res[name].targets]
 
 
+def test_multi_camera_batch_matches_the_oracle_per_camera():
+    """CameraBatch.step against the CPU oracle itself (not against the CUDA path): every camera's rows equal
+    oracle.detect(frame) of that camera — the fp32-accurate detector mode so that the comparison is at the north-star bar
+    (same rows in the same order, class ids equal, boxes within 0.25 px, scores within 1e-3); frames of two shapes, so two
+    detect_batch groups per step (clearcam.py:580-585 semantics per camera)."""
+    from clearcam_b200.cameras import CameraBatch
+    fr, x, P = _setup("t", 320, 3, 240, 320, seed=2)
+    wide = o.synthetic_frames(2, 180, 320, seed=7)
+    m = YOLOv9("t", 320, weights=P, precise=True)
+    cb = CameraBatch(m)
+    frames = {f"a{i}": fr[i].numpy() for i in range(3)}
+    frames.update({f"w{i}": wide[i].numpy() for i in range(2)})
+    res = cb.step(frames)
+    assert set(res) == set(frames)
+    n_rows = 0
+    for name, f in frames.items():
+        want = o.detect("t", P, torch.from_numpy(f)[None], 320)[0]
+        got = torch.from_numpy(res[name].rows)
+        A, G = want[want[:, 4] > 0], got[got[:, 4] > 0]
+        n_rows += len(A)
+        if len(A) == len(G) and len(A) and bool((A[:, 5] == G[:, 5]).all()):
+            assert float((A[:, :4] - G[:, :4]).abs().max()) <= 0.25 and float((A[:, 4] - G[:, 4]).abs().max()) <= 1e-3, name
+        else:           # a score at the 0.25 threshold or a pair at the IoU 0.45 boundary: compare as sets
+            frac, _ = _match(want, got)
+            assert frac >= 0.95 and abs(len(A) - len(G)) <= 1, (name, len(A), len(G), frac)
+    assert n_rows > 0
+
+
 def test_mailbox_ingest_feeds_the_batched_detector():
     """rawvideo bytes -> pinned FrameMailbox slots -> CameraBatch.step_mailboxes == model(frame) per camera."""
     import io
