@@ -950,18 +950,29 @@ budget_again:
       p.b_res = 0;
     }
     int wbytes;
+    bool deep = false;      // weight ring deep enough to cover the L2 latency
     if (p.b_res) { wbytes = bres_bytes; S = 2; }
     else {
+      // Streamed weights: the weight ring must cover the L2 latency — one k-block consumes a b_bytes stage per 2*BN tensor
+      // cycles (64 B/clk whatever BN is), and at ~1200 cycles of latency that is ~80 KB in flight.  With three 16-KB stages
+      // (BN = 128) the 3x3 128->128 convs ran at 57 % of their tensor time, and halving the bytes per CTA (pair multicast) did
+      // not move them: the depth was the limit.  A halo buffer, in contrast, holds nine k-blocks of work, so two of them are
+      // enough to prefetch one chunk ahead: weight stages are bought before the third halo buffer.
+      static const int bdepth_env = getenv("CC_B_INFLIGHT_KB") ? atoi(getenv("CC_B_INFLIGHT_KB")) : 80;
+      const int want = (bdepth_env * 1024 + b_bytes - 1) / b_bytes;
       S = 3;
-      while (S < 6 && avail - (S + 1) * b_bytes >= 3 * p.halo_bytes) ++S;   // extra weight stages only once 3 halo buffers fit
+      while (S < 8 && S < want && avail - (S + 1) * b_bytes >= 2 * p.halo_bytes) ++S;
+      while (S < 6 && avail - (S + 1) * b_bytes >= 3 * p.halo_bytes) ++S;   // more of both where there is room
       wbytes = S * b_bytes;
+      deep = S >= want;
     }
     int hs = (avail - wbytes) / p.halo_bytes;
     if (hs > 4) hs = 4;
     if (hst_env >= 2 && hst_env <= 4 && hst_env < hs) hs = hst_env;
-    if (hs < 3 && nbuf == 2) { nbuf = 1; goto budget_again; }
-    if (hs < 3 && p.colsplit) { cs = 0; nbuf = nbuf_env == 1 ? 1 : 2; goto budget_again; }   // K-heavy 3x3 tiles: the mainloop matters more
-    if (hs < 3 && level == 0) {   // the staging squeezes the halo ring: halve it (an MMA-bound layer does not need more)
+    const bool depth_ok = hs >= 3 || (hs >= 2 && deep);
+    if (!depth_ok && nbuf == 2) { nbuf = 1; goto budget_again; }
+    if (!depth_ok && p.colsplit) { cs = 0; nbuf = nbuf_env == 1 ? 1 : 2; goto budget_again; }   // K-heavy 3x3 tiles: the mainloop matters more
+    if (!depth_ok && level == 0) {   // the staging squeezes the operand rings: halve it (an MMA-bound layer does not need more)
       level = 1;
       goto budget_again;
     }
