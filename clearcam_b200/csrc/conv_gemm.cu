@@ -479,6 +479,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       else { pw = w0 + (row & TWm); ph = h0 + ((row >> p.lTW) & THm); pn = n0 + (row >> (p.lTW + p.lTH)); }
       const bool pvalid = (pw < p.W) && (ph < p.H) && (pn < p.N);
       const long long ppix = static_cast<long long>(pn) * p.out_ns + ph * p.W + pw;
+      // pre-activation addend from a half-resolution fp32 map (nearest x2 upsample by addressing): this pixel's source row
+      const float* const pre_row = (p.pre != nullptr && pvalid)
+          ? p.pre + ((static_cast<long long>(pn) * p.pre_h + (ph >> 1)) * p.pre_w + (pw >> 1)) * p.cout : nullptr;
 
       mbar_wait(&tfull_bar[acc], acc_par);
       tc_fence_after();
@@ -513,7 +516,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           float f[16];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float4 b4 = lds_f4(sbias32 + (gcol + 4 * j) * 4);
+            float4 b4 = lds_f4(sbias32 + (gcol + 4 * j) * 4);
+            if (pre_row != nullptr) {
+              const float4 q4 = __ldg(reinterpret_cast<const float4*>(pre_row + gcol) + j);
+              b4.x += q4.x; b4.y += q4.y; b4.z += q4.z; b4.w += q4.w;
+            }
             f[4 * j] = act_apply<ACT>(__uint_as_float(v[4 * j]) + b4.x);
             f[4 * j + 1] = act_apply<ACT>(__uint_as_float(v[4 * j + 1]) + b4.y);
             f[4 * j + 2] = act_apply<ACT>(__uint_as_float(v[4 * j + 2]) + b4.z);
@@ -856,6 +863,8 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
   p.bias = d.bias; p.act = d.act;
   p.res = d.res; p.res_cs = d.res_cs; p.res_co = d.res_co;
   p.out_ns = d.out_ns > 0 ? d.out_ns : Hout * Wout;
+  p.pre = d.pre; p.pre_h = d.pre_h; p.pre_w = d.pre_w;
+  if (d.pre) CC_REQUIRE(d.pre_h * 2 == Hout && d.pre_w * 2 == Wout && d.Cout % 4 == 0, "conv_gemm: the pre-activation addend must be a half-resolution map of the output");
 
   // ---- epilogue groups / staging / smem budget -> pipeline depth
   // Preferred: 4 groups of 4 warps with 16-KB staging each (BN <= 128: four 128-column TMEM slots), 2 groups of 8 warps

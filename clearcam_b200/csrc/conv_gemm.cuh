@@ -59,6 +59,8 @@ struct GemmParams {
   int32_t pair, n_super;              // enabled / number of (M-tile pair, N block) super tiles
   int32_t CH;                         // output columns per staging pass of one epilogue group
   int32_t stg_nbuf;                   // staging buffers per epilogue group (1 or 2)
+  const float* pre;                   // optional fp32 [N][H/2][W/2][Cout]: added BEFORE the activation at (n, h/2, w/2) — a 1x1 conv over
+  int32_t pre_h, pre_w;               //   concat(upsample(a), b) is computed as conv_b(b) + upsample(conv_a(a)) (see yolo.cu)
   int32_t n_grp, colsplit;            // epilogue groups; 1: every group converts its share of the columns of EVERY tile
   unsigned long long* trace;          // optional device timeline slots [8] (globaltimer ns): first CTA entry, dependency released, last CTA exit,
                                       // and of CTA 0: first operands landed, all MMAs issued, first accumulator complete, last epilogue done, exit
@@ -75,6 +77,7 @@ struct ConvDesc {
   const void* res; int res_cs, res_co;
   int bn_override;                         // 0 = heuristic
   int out_ns;                              // 0 = Hout*Wout; else pixels per image in the out/residual buffers
+  const float* pre; int pre_h, pre_w;      // optional half-resolution fp32 pre-activation addend (see GemmParams::pre)
 };
 
 struct GemmLaunch {

@@ -52,6 +52,10 @@ int avgpool2_pad_launch(const TSlice& in, const TSlice& out, cudaStream_t s);
 int avgmax_pool_launch(const TSlice& in, const TSlice& out, cudaStream_t s);
 // max_pool2d(k=5,s=1,p=2)  (SP, detection/yolov9.py:127-132)
 int maxpool5_launch(const TSlice& in, const TSlice& out, cudaStream_t s);
+// the three cascaded SP pools of SPPELAN (detection/yolov9.py:134-149) in one launch: reads channels [0, c1) of the concat
+// buffer `cat`, writes [c1, 2c1), [2c1, 3c1), [3c1, 4c1)
+bool spp3_supported(const TSlice& cat, int c1);
+int spp3_launch(const TSlice& cat, int c1, cudaStream_t s);
 // nearest x2 upsample (Upsample, detection/yolov9.py:285-292)
 int upsample2_launch(const TSlice& in, const TSlice& out, cudaStream_t s);
 // CBFuse (detection/yolov9.py:230-245): out = sum_i nearest_resize(src_i) + last

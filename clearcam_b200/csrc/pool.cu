@@ -246,6 +246,71 @@ int maxpool5_launch(const TSlice& in, const TSlice& out, cudaStream_t s) {
   return CC_OK;
 }
 
+// ---------------------------------------------------------------- SPP: three cascaded 5x5 max pools in one launch
+// SPPELAN (detection/yolov9.py:134-149) max-pools its cv1 output three times in a row (5x5, s1, p2) and concatenates all four
+// maps.  At 20x20 the three launches were latency, not work (3 x ~18 us for 13 MB).  One block per (image, 64-channel block)
+// keeps the map in shared memory, runs each pool separably (row max, column max: exact, max does not round) and writes the
+// three results into their channel slices of the concat buffer.  Requires H*W*128 B * 2 buffers of shared memory.
+__device__ __forceinline__ uint4 max_bf16x8(uint4 a, uint4 b) {
+  uint4 r;
+  __nv_bfloat162* pa = reinterpret_cast<__nv_bfloat162*>(&a);
+  __nv_bfloat162* pb = reinterpret_cast<__nv_bfloat162*>(&b);
+  __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+  return r;
+}
+__global__ void __launch_bounds__(256) spp3_kernel(TSlice cat, int c1) {
+  extern __shared__ uint4 spp_smem[];
+  const int HW = cat.H * cat.W, W = cat.W, H = cat.H;
+  uint4* sA = spp_smem;             // [HW][8] current map
+  uint4* sB = spp_smem + HW * 8;    // [HW][8] row maxima
+  const int n = blockIdx.y, c0 = blockIdx.x * 64;
+  const __nv_bfloat16* src = cat.p + static_cast<long long>(n) * HW * cat.cs + cat.co + c0;
+  for (int i = threadIdx.x; i < HW * 8; i += 256) {
+    const int px = i >> 3, v = i & 7;
+    sA[i] = __ldg(reinterpret_cast<const uint4*>(src + static_cast<long long>(px) * cat.cs + v * 8));
+  }
+  __syncthreads();
+  for (int pass = 1; pass <= 3; ++pass) {
+    for (int i = threadIdx.x; i < HW * 8; i += 256) {
+      const int px = i >> 3, v = i & 7, y = px / W, x = px - y * W;
+      uint4 m = sA[i];
+#pragma unroll
+      for (int dx = -2; dx <= 2; ++dx)
+        if (dx != 0 && x + dx >= 0 && x + dx < W) m = max_bf16x8(m, sA[(px + dx) * 8 + v]);
+      sB[i] = m;
+    }
+    __syncthreads();
+    __nv_bfloat16* dst = cat.p + static_cast<long long>(n) * HW * cat.cs + cat.co + pass * c1 + c0;
+    for (int i = threadIdx.x; i < HW * 8; i += 256) {
+      const int px = i >> 3, v = i & 7, y = px / W;
+      uint4 m = sB[i];
+#pragma unroll
+      for (int dy = -2; dy <= 2; ++dy)
+        if (dy != 0 && y + dy >= 0 && y + dy < H) m = max_bf16x8(m, sB[(px + dy * W) * 8 + v]);
+      sA[i] = m;                    // (every thread rewrites only its own element: readers of sA are behind the barrier above)
+      *reinterpret_cast<uint4*>(dst + static_cast<long long>(px) * cat.cs + v * 8) = m;
+    }
+    __syncthreads();
+  }
+}
+bool spp3_supported(const TSlice& cat, int c1) {
+  return !cat.f32 && c1 % 64 == 0 && cat.co % 8 == 0 && cat.cs % 8 == 0 && static_cast<size_t>(cat.H) * cat.W * 128 * 2 <= 200 * 1024;
+}
+int spp3_launch(const TSlice& cat, int c1, cudaStream_t s) {
+  CC_REQUIRE(spp3_supported(cat, c1) && cat.C >= 4 * c1, "spp3: unsupported slice");
+  const int smem = cat.H * cat.W * 128 * 2;
+  static int attr_max = 0;
+  if (smem > attr_max) {
+    CC_CHECK_CUDA(cudaFuncSetAttribute(spp3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_max = smem;
+  }
+  spp3_kernel<<<dim3(c1 / 64, cat.N), 256, smem, s>>>(cat, c1);
+  CC_CHECK_CUDA(cudaGetLastError());
+  return CC_OK;
+}
+
 // ---------------------------------------------------------------- nearest x2
 template <typename E>
 __global__ void upsample2_kernel(TSlice in, TSlice out) {

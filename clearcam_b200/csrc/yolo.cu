@@ -162,7 +162,7 @@ static __nv_bfloat16 f2bf(float x) { return __float2bfloat16_rn(x); }
 struct T { __nv_bfloat16* p = nullptr; int cs = 0, co = 0, C = 0, H = 0, W = 0; bool image = false; bool f32 = false; };   // f32: p is really float*
 
 struct Op {
-  enum Kind { GEMM, DIRECT, AVGPAD, AVGMAX, MAXPOOL5, UPSAMPLE, CBFUSE, LETTERBOX, STEM, STEM_IM2COL, STEM_TC, DECODE, POST, SPLIT, FINISH } kind;
+  enum Kind { GEMM, DIRECT, AVGPAD, AVGMAX, MAXPOOL5, UPSAMPLE, CBFUSE, LETTERBOX, STEM, STEM_IM2COL, STEM_TC, DECODE, POST, SPLIT, FINISH, SPP3 } kind;
   GemmLaunch gemm;
   DirectConvParams direct;
   TSlice s_in, s_out;
@@ -225,9 +225,12 @@ struct YoloModel {
 
   // Load conv `name` (PyTorch layout [Cout][Cin/g][k][k]) -> [Cout][k][k][Cin] bf16, optionally expanding groups
   // to block-diagonal dense, optionally stacking a second conv's output channels under it (fused 1x1 pair).
+  // ci_begin / ci_total: load only input channels [ci_begin, ci_begin + cin) of a conv stored with ci_total input channels (the
+  // two halves of a 1x1 conv over a concat); with_bias = false leaves the bias zero (it is applied once, by the other half)
   int load_conv(const std::string& key, const std::vector<std::string>& names, int cin, const std::vector<int>& couts,
-                int k, int groups, bool dense, bool stem = false) {
+                int k, int groups, bool dense, bool stem = false, int ci_begin = 0, int ci_total = 0, bool with_bias = true) {
     if (convs.count(key)) return CC_OK;
+    if (ci_total == 0) ci_total = cin;
     int cout_total = 0;
     for (int c : couts) cout_total += c;
     const int cin_g = cin / groups;
@@ -240,9 +243,11 @@ struct YoloModel {
       auto iw = host.find(names[t] + ".weight"), ib = host.find(names[t] + ".bias");
       CC_REQUIRE(iw != host.end() && ib != host.end(), "yolo: missing weight '%s'", names[t].c_str());
       const int cout = couts[t];
-      CC_REQUIRE(iw->second.n == static_cast<long long>(cout) * cin_g * k * k && ib->second.n == cout,
+      const int src_cin_g = ci_total / groups;
+      CC_REQUIRE(iw->second.n == static_cast<long long>(cout) * src_cin_g * k * k && ib->second.n == cout,
                  "yolo: '%s' has %lld weight / %lld bias elements, expected %lld / %d", names[t].c_str(), iw->second.n,
-                 ib->second.n, static_cast<long long>(cout) * cin_g * k * k, cout);
+                 ib->second.n, static_cast<long long>(cout) * src_cin_g * k * k, cout);
+      CC_REQUIRE(ci_total == cin || groups == 1, "yolo: '%s': an input-channel sub-range of a grouped conv", names[t].c_str());
       const float* src = iw->second.p;
       const int cpg_out = cout / groups;
       for (int co = 0; co < cout; ++co) {
@@ -250,12 +255,12 @@ struct YoloModel {
         for (int ci = 0; ci < cin_g; ++ci)
           for (int r = 0; r < k; ++r)
             for (int s = 0; s < k; ++s) {
-              const float v = src[((static_cast<size_t>(co) * cin_g + ci) * k + r) * k + s];
+              const float v = src[((static_cast<size_t>(co) * src_cin_g + ci_begin + ci) * k + r) * k + s];
               const int ci_eff = dense ? g * cin_g + ci : ci;
               if (stem) wf[(static_cast<size_t>(co_base + co) * 9 + r * 3 + s) * 3 + ci] = v;
               else w[((static_cast<size_t>(co_base + co) * k + r) * k + s) * cin_eff + ci_eff] = f2bf(v);
             }
-        bias[co_base + co] = ib->second.p[co];
+        bias[co_base + co] = with_bias ? ib->second.p[co] : 0.f;
       }
       co_base += cout;
     }
@@ -366,7 +371,7 @@ struct Builder {
 
   // conv: in -> out slice (out.H/W must already be the conv's output extent)
   void conv(const std::string& key, const T& in, const T& out, int stride, int act, const T* res = nullptr,
-            float* out_f32 = nullptr) {
+            float* out_f32 = nullptr, const float* pre = nullptr, int pre_h = 0, int pre_w = 0) {
     if (rc) return;
     auto it = M.convs.find(key);
     if (it == M.convs.end()) { set_error("yolo plan: conv '%s' not loaded", key.c_str()); rc = CC_ERR_STATE; return; }
@@ -430,6 +435,7 @@ struct Builder {
       else { d.out = out.p; d.out_cs = out.cs; d.out_co = out.co; d.out_f32 = 0; }
       d.Cout = cw.cout; d.act = act;
       if (res) { d.res = res->p; d.res_cs = res->cs; d.res_co = res->co; }
+      d.pre = pre; d.pre_h = pre_h; d.pre_w = pre_w;
       op.kind = Op::GEMM;
       rc = conv_gemm_build(d, M.sms, &op.gemm);
       if (rc) return;
@@ -504,6 +510,24 @@ static int layer_out_channels(const Layer& l, const std::vector<int>& outC, int 
   return 0;
 }
 
+// Upsample -> Concat(-1, skip) -> RepNCSPELAN4: the block's first conv is a 1x1 over concat(upsample(a), b), and a 1x1 conv
+// commutes with nearest upsampling: silu(W [up(a); b] + bias) = silu(up(W_a a) + W_b b + bias).  So W_a runs at HALF resolution
+// (a quarter of its FLOPs) into a small fp32 map, and the full-resolution conv over b alone adds it before the activation by
+// addressing (GemmParams::pre): the upsample kernel, the concat buffer and half of the conv's input traffic disappear
+// (detection/yolov9.py:285-292, :107-125; layers 10-12 and 13-15 of t/s/m/c, 30-32 and 33-35 of e).
+static bool fuse_up_concat(const std::vector<Layer>& S, const std::vector<int>& outC, int i, bool precise, int* c_up = nullptr) {
+  static const int env = getenv("CC_FUSE_UP") ? atoi(getenv("CC_FUSE_UP")) : 1;
+  if (!env || precise || i < 3) return false;
+  const Layer& e = S[i];
+  if (e.op != L_ELAN4 || e.f.size() != 1 || e.f[0] != -1) return false;
+  const Layer& c = S[i - 1];
+  if (c.op != L_CONCAT || c.f[0] != -1 || S[i - 2].op != L_UPSAMPLE || S[i - 2].f[0] != -1) return false;
+  const int cu = outC[i - 2], cskip = outC[i - 1] - cu;
+  if (cu % 16 || cskip % 16 || cu <= 0 || cskip <= 0 || (4 * e.b) % 16) return false;
+  if (c_up) *c_up = cu;
+  return true;
+}
+
 int Builder::build() {
   const std::vector<Layer>& S = M.spec;
   const int nl = static_cast<int>(S.size());
@@ -513,6 +537,7 @@ int Builder::build() {
   for (int i = 0; i < nl; ++i)
     if (S[i].op == L_CONCAT) {
       const int a = S[i].f[0] == -1 ? i - 1 : S[i].f[0], b = S[i].f[1] == -1 ? i - 1 : S[i].f[1];
+      if (i + 1 < nl && fuse_up_concat(S, outC, i + 1, M.precise)) continue;   // never materialised
       if (!place.count(a) && !place.count(b) && S[a].op != L_SILENCE && S[b].op != L_SILENCE) {
         place[a] = {i, 0};
         place[b] = {i, outC[a]};
@@ -635,7 +660,26 @@ int Builder::build() {
         // detection/yolov9.py:107-125
         const int b = l.b;
         T cat = talloc(8 * b, in.H, in.W);
-        conv(pfx + ".cv1", in, slice(cat, 0, 4 * b), 1, CC_ACT_SILU);
+        if (fuse_up_concat(S, outC, i, M.precise)) {
+          const T& lo = outs[i - 3];                       // the Upsample layer's source
+          const T& hi = src(S[i - 1].f[1]);                // the Concat's second source
+          float* part = static_cast<float*>(dalloc(static_cast<size_t>(P.B) * lo.H * lo.W * 4 * b * 4));
+          T dummy;
+          conv(pfx + ".cv1.lo", lo, dummy, 1, CC_ACT_NONE, nullptr, part);
+          conv(pfx + ".cv1.hi", hi, slice(cat, 0, 4 * b), 1, CC_ACT_SILU, nullptr, nullptr, part, lo.H, lo.W);
+          if (!rc && !bump.dry && P.ops.size() >= 2) {
+            // algorithmic FLOPs: the pair replaces ONE 1x1 conv over all input channels at full resolution (what the reference
+            // computes and SURVEY 8(d) counts); booked on the full-resolution launch, the half-resolution one carries none
+            GemmLaunch& g_hi = P.ops[P.ops.size() - 1].gemm;
+            GemmLaunch& g_lo = P.ops[P.ops.size() - 2].gemm;
+            const double full = 2.0 * P.B * in.H * in.W * double(4 * b) * in.C;
+            P.conv_flops += full - g_hi.flops - g_lo.flops;
+            g_hi.flops = full;
+            g_lo.flops = 0.0;
+          }
+        } else {
+          conv(pfx + ".cv1", in, slice(cat, 0, 4 * b), 1, CC_ACT_SILU);
+        }
         T r1 = repncsp(pfx + ".cv2.0", slice(cat, 2 * b, 2 * b), b, l.n);
         conv(pfx + ".cv2.1", r1, slice(cat, 4 * b, 2 * b), 1, CC_ACT_SILU);
         T r2 = repncsp(pfx + ".cv3.0", slice(cat, 4 * b, 2 * b), b, l.n);
@@ -670,17 +714,31 @@ int Builder::build() {
         const int c1 = l.b;
         T cat = talloc(4 * c1, in.H, in.W);
         conv(pfx + ".cv1", in, slice(cat, 0, c1), 1, CC_ACT_SILU);
-        for (int q = 0; q < 3; ++q) simple(Op::MAXPOOL5, slice(cat, q * c1, c1), slice(cat, (q + 1) * c1, c1), "spp.max5");
+        static const int spp3_env = getenv("CC_SPP3") ? atoi(getenv("CC_SPP3")) : 1;
+        if (spp3_env && spp3_supported(ts(cat), c1)) {
+          if (!rc && !bump.dry) { Op op; op.kind = Op::SPP3; op.s_in = ts(cat); op.s_out = ts(cat); op.s_out.C = c1; op.name = "spp.max5x3"; P.ops.push_back(std::move(op)); }
+        } else {
+          for (int q = 0; q < 3; ++q) simple(Op::MAXPOOL5, slice(cat, q * c1, c1), slice(cat, (q + 1) * c1, c1), "spp.max5");
+        }
         out = out_for(i, l.c, in.H, in.W);
         conv(pfx + ".cv5", cat, out, 1, CC_ACT_SILU);
         break;
       }
       case L_UPSAMPLE: {
+        if (i + 2 < nl && fuse_up_concat(S, outC, i + 2, M.precise)) {     // folded into the consumer's first conv: shape only
+          out = T{}; out.C = in.C; out.H = in.H * 2; out.W = in.W * 2;
+          break;
+        }
         out = out_for(i, in.C, in.H * 2, in.W * 2);
         simple(Op::UPSAMPLE, in, out, "upsample");
         break;
       }
       case L_CONCAT: {
+        if (i + 1 < nl && fuse_up_concat(S, outC, i + 1, M.precise)) {     // shape only (see fuse_up_concat)
+          const T& skip = src(l.f[1]);
+          out = T{}; out.C = outC[i]; out.H = skip.H; out.W = skip.W;
+          break;
+        }
         if (concat_buf.count(i)) { out = concat_buf[i]; break; }
         // fallback (a source was already placed elsewhere): explicit copy through 1:1 "upsample"-free path not needed
         // for the reference graphs; refuse rather than silently mis-route.
@@ -782,6 +840,7 @@ static int plan_run(YoloPlan& P, const void* d_frames, float* d_out, float* d_ra
       case Op::AVGMAX: rc = avgmax_pool_launch(op.s_in, op.s_out, st); break;
       case Op::MAXPOOL5: rc = maxpool5_launch(op.s_in, op.s_out, st); break;
       case Op::UPSAMPLE: rc = upsample2_launch(op.s_in, op.s_out, st); break;
+      case Op::SPP3: rc = spp3_launch(op.s_in, op.s_out.C, st); break;
       case Op::CBFUSE: rc = cbfuse_launch(op.cbf, st); break;
       case Op::LETTERBOX: { LetterboxParams q = op.lb; q.in = d_frames; rc = letterbox_launch(q, st); break; }
       case Op::STEM: { StemParams q = op.stem; if (!q.in) q.in = d_frames; rc = stem_launch(q, st); break; }
@@ -809,7 +868,7 @@ static const char* op_kind_name(Op::Kind k) {
     case Op::GEMM: return "conv_gemm"; case Op::DIRECT: return "conv_direct"; case Op::AVGPAD: return "avgpool2_pad";
     case Op::AVGMAX: return "avgmax_pool"; case Op::MAXPOOL5: return "maxpool5"; case Op::UPSAMPLE: return "upsample2";
     case Op::CBFUSE: return "cbfuse"; case Op::LETTERBOX: return "letterbox"; case Op::STEM: return "stem"; case Op::STEM_IM2COL: return "stem_im2col"; case Op::STEM_TC: return "stem_tc";
-    case Op::DECODE: return "decode"; case Op::POST: return "postprocess"; case Op::SPLIT: return "split_planes"; case Op::FINISH: return "finish_f32";
+    case Op::DECODE: return "decode"; case Op::POST: return "postprocess"; case Op::SPLIT: return "split_planes"; case Op::FINISH: return "finish_f32"; case Op::SPP3: return "spp3";
   }
   return "?";
 }
@@ -843,13 +902,15 @@ int cc_yolo_create_ex(const char* size, int flags, int n_tensors, const char* co
 
   int rc = CC_OK;
   auto L = [&](const std::string& key, std::vector<std::string> nm, int cin, std::vector<int> couts, int k, int g = 1,
-               bool stem = false) {
+               bool stem = false, int ci_begin = 0, int ci_total = 0, bool with_bias = true) {
     if (rc) return;
     int ct = 0;
     for (int c : couts) ct += c;
     const bool dense = tc_ok(cin, ct);   // grouped convs ride the tensor-core kernel as block-diagonal dense
-    rc = M.load_conv(key, nm, cin, couts, k, g, dense || g == 1, stem);
+    rc = M.load_conv(key, nm, cin, couts, k, g, dense || g == 1, stem, ci_begin, ci_total, with_bias);
   };
+  std::vector<int> outC(M.spec.size(), 0);
+  for (size_t i = 0; i < M.spec.size(); ++i) outC[i] = layer_out_channels(M.spec[i], outC, static_cast<int>(i));
   auto repncsp = [&](const std::string& p, int a, int b, int n) {
     L(p + ".cv1+cv2", {p + ".cv1.conv", p + ".cv2.conv"}, a, {b, b}, 1);
     L(p + ".cv3", {p + ".cv3.conv"}, a, {a}, 1);
@@ -870,14 +931,21 @@ int cc_yolo_create_ex(const char* size, int flags, int n_tensors, const char* co
         L(p + ".cv3", {p + ".cv3.conv"}, l.c, {l.c}, 3);
         L(p + ".cv4", {p + ".cv4.conv"}, l.n, {l.b}, 1);
         break;
-      case L_ELAN4:
-        L(p + ".cv1", {p + ".cv1.conv"}, l.a, {4 * l.b}, 1);
+      case L_ELAN4: {
+        int c_up = 0;
+        if (fuse_up_concat(M.spec, outC, static_cast<int>(i), M.precise, &c_up)) {   // the two input-channel halves of cv1
+          L(p + ".cv1.lo", {p + ".cv1.conv"}, c_up, {4 * l.b}, 1, 1, false, 0, l.a, false);
+          L(p + ".cv1.hi", {p + ".cv1.conv"}, l.a - c_up, {4 * l.b}, 1, 1, false, c_up, l.a, true);
+        } else {
+          L(p + ".cv1", {p + ".cv1.conv"}, l.a, {4 * l.b}, 1);
+        }
         repncsp(p + ".cv2.0", 2 * l.b, l.b, l.n);
         L(p + ".cv2.1", {p + ".cv2.1.conv"}, 2 * l.b, {2 * l.b}, 3);
         repncsp(p + ".cv3.0", 2 * l.b, l.b, l.n);
         L(p + ".cv3.1", {p + ".cv3.1.conv"}, 2 * l.b, {2 * l.b}, 3);
         L(p + ".cv4", {p + ".cv4.conv"}, 8 * l.b, {l.c}, 1);
         break;
+      }
       case L_ADOWN:
         L(p + ".cv1", {p + ".cv1.conv"}, l.a, {l.a}, 3);
         L(p + ".cv2", {p + ".cv2.conv"}, l.a, {l.a}, 1);
@@ -1130,7 +1198,7 @@ int cc_yolo_layer_output(cc_yolo* h, int is_f32, int B, int Hf, int Wf, int res,
   if (rc) return rc;
   CC_REQUIRE(layer >= 0 && layer < static_cast<int>(P->layer_outs.size()), "cc_yolo_layer_output: bad layer %d", layer);
   const T& t = P->layer_outs[layer];
-  if (C) *C = t.image ? 0 : t.C;
+  if (C) *C = (t.image || !t.p) ? 0 : t.C;      // layers folded into their consumer have a shape but no tensor
   if (H) *H = t.H;
   if (W) *W = t.W;
   if (!d_dst || t.image || !t.p) return CC_OK;
