@@ -59,7 +59,7 @@ int spp3_launch(const TSlice& cat, int c1, cudaStream_t s);
 // nearest x2 upsample (Upsample, detection/yolov9.py:285-292)
 int upsample2_launch(const TSlice& in, const TSlice& out, cudaStream_t s);
 // CBFuse (detection/yolov9.py:230-245): out = sum_i nearest_resize(src_i) + last
-struct CBFuseParams { TSlice src[5]; int nsrc; TSlice last; TSlice out; };
+struct CBFuseParams { TSlice src[5]; int nsrc; TSlice last; TSlice out; int shift[5]; };   // shift: filled by the launcher (log2 of out/src, -1 = general)
 int cbfuse_launch(const CBFuseParams& p, cudaStream_t s);
 
 // Letterbox: bilinear resize (utils/helpers.py:127-131 semantics, W axis first then H, result cast to the

@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(256, 2) avgmax_pool_kernel(TSlice in, TSlice o
               // the reference max-pools the STORED (rounded) avg map; rounding to the storage type is monotonic, so
               // max(round(a_i)) == round(max(a_i)) and the one rounding happens in the final store (nine bf16 conversions
               // per element kept this kernel bound by the conversion unit: ncu sm__inst_executed_pipe_xu 37 %)
-              m[i] = fmaxf(m[i], (hp[c][i] + h[c][i]) * 0.25f);
+              m[i] = fmaxf(m[i], hp[c][i] + h[c][i]);          // (x 0.25 after the max: an exact scaling commutes with it)
             }
           }
         }
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(256, 2) avgmax_pool_kernel(TSlice in, TSlice o
   }
   bf8 o;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) o.v[i] = m[i];
+  for (int i = 0; i < 8; ++i) o.v[i] = m[i] * 0.25f;
   Vec8<E>::st(at_w<E>(out, q.n, q.h, q.w, q.c), o);
 }
 int avgmax_pool_launch(const TSlice& in, const TSlice& out, cudaStream_t s) {
@@ -341,9 +341,11 @@ __global__ void cbfuse_kernel(CBFuseParams p) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc.v[i] = 0.f;
   for (int k = 0; k < p.nsrc; ++k) {
-    // nearest: src = floor(dst * in / out)
-    const int sh = (q.h * p.src[k].H) / p.out.H;
-    const int sw = (q.w * p.src[k].W) / p.out.W;
+    // nearest: src = floor(dst * in / out); the maps of the reference graphs are power-of-two multiples of each other, so
+    // the host passes the ratio as a shift (two integer divisions per source per thread made this kernel instruction-bound:
+    // 1.5 TB/s at 320x320)
+    const int sh = p.shift[k] >= 0 ? (q.h >> p.shift[k]) : (q.h * p.src[k].H) / p.out.H;
+    const int sw = p.shift[k] >= 0 ? (q.w >> p.shift[k]) : (q.w * p.src[k].W) / p.out.W;
     const bf8 a = Vec8<E>::ld(at<E>(p.src[k], q.n, sh, sw, q.c));
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc.v[i] = (k == 0) ? a.v[i] : acc.v[i] + a.v[i];
@@ -353,8 +355,14 @@ __global__ void cbfuse_kernel(CBFuseParams p) {
   for (int i = 0; i < 8; ++i) acc.v[i] += l.v[i];
   Vec8<E>::st(at_w<E>(p.out, q.n, q.h, q.w, q.c), acc);
 }
-int cbfuse_launch(const CBFuseParams& p, cudaStream_t s) {
+int cbfuse_launch(const CBFuseParams& p0, cudaStream_t s) {
+  CBFuseParams p = p0;
   CC_REQUIRE(p.nsrc >= 1 && p.nsrc <= 5 && p.out.C % 8 == 0, "cbfuse: bad params");
+  for (int k = 0; k < p.nsrc; ++k) {
+    p.shift[k] = -1;
+    for (int sft = 0; sft < 8; ++sft)
+      if ((p.src[k].H << sft) == p.out.H && (p.src[k].W << sft) == p.out.W) p.shift[k] = sft;
+  }
   CC_REQUIRE(p.out.H <= 65535 && p.out.N <= 65535, "cbfuse: tensor too large for the row grid");
   const int t = row_threads(p.out);
   CC_LAUNCH_E(cbfuse_kernel, p.out.f32, row_grid(p.out, t), t, s, p);
