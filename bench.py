@@ -424,7 +424,7 @@ def yolo_section(cx, with_cpu):
                 "per_kind_ms_events": {k: round(v["ms"], 4) for k, v in by.items()}}
         cpu = None
         if with_cpu:                   # rank 0 at N=1 only: the other ranks must not sit in a barrier
-            cpu = cpu_pool("yolo", P, steps=6, warmup=2)
+            cpu = cpu_pool("yolo", P, steps=16, warmup=2)              # ~64 frames, ~10 s: the same order as the reference arm at the driver's K
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
             cpu["parity_sample"] = parity_sample(model, P)
         line = {"metric": "frames/s YOLOv9-c 640px", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K,
@@ -524,9 +524,9 @@ def clip_section(cx, with_cpu, archs=(("ViT-B/32", 256), ("ViT-L/14", 256))):
                              "attention": {"ms": ams, "tflops": afl / max(ams, 1e-9) / 1e9, "share_of_step": ams / sum(o_["ms"] for o_ in ops)},
                              "other_kernels_ms": sum(o_["ms"] for o_ in other)}
             if with_cpu and arch == "ViT-B/32":
-                c = cpu_pool("clip", P, steps=6, warmup=2)
+                c = cpu_pool("clip", P, steps=16, warmup=2)
                 r["cpu_baseline"] = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")}
-                c = cpu_pool("clip-text", P, steps=6, warmup=2)
+                c = cpu_pool("clip-text", P, steps=16, warmup=2)
                 r["text"]["cpu_baseline"] = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")}
         res[arch] = r
         del cm, fin, xs, P

@@ -29,6 +29,7 @@ struct AttnParams {
   const __nv_bfloat16* qkv;
   __nv_bfloat16* ctx;
   int B, L, Lk, H, W, causal;
+  int vmajor;      // 1: V is read in place from the QKV buffer ([key][64 d] tiles = an MN-major B operand); 0: from the V^T pre-pass
   int tail;        // 1: one image per CTA and L = 128 n + 1 -> the last token runs on CUDA cores (warp 9)
   int G;           // images per CTA (packed sequence of G*L tokens, Lk = ceil(G*L / 64) * 64 key columns)
   int tmem_cols;   // power of two >= Lk + 64
@@ -118,7 +119,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tc_kernel(const __g
       mbar_arrive_expect_tx(bar_k, p.Lk * 128);
       for (int j = 0; j < nkb; ++j) tma_load_2d(sK + j * 8192, &p.tmQK, bar_k, p.W + h * 64, row0 + 64 * j);
       mbar_arrive_expect_tx(bar_v, nkb * 8192);
-      for (int j = 0; j < nkb; ++j) tma_load_2d(sV + j * 8192, &p.tmVt, bar_v, 64 * j, bh * 64);
+      for (int j = 0; j < nkb; ++j) {
+        if (p.vmajor) tma_load_2d(sV + j * 8192, &p.tmQK, bar_v, 2 * p.W + h * 64, row0 + 64 * j);   // V rows as they are: [key][64 d]
+        else tma_load_2d(sV + j * 8192, &p.tmVt, bar_v, 64 * j, bh * 64);
+      }
       if (nqb > 0) {
         mbar_arrive_expect_tx(bar_q, 128 * 128);
         tma_load_2d(sQ, &p.tmQK, bar_q, h * 64, row0);
@@ -129,7 +133,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tc_kernel(const __g
     const int nch = (p.Lk + 255) >> 8;             // N chunks of the first MMA (N <= 256 each)
     const int chN = p.Lk / nch;
     const uint32_t idesc_s = umma_idesc_f16(128, chN, 1);
-    const uint32_t idesc_o = umma_idesc_f16(128, 64, 1);
+    // O = P . V: B operand = V.  From the V^T pre-pass it is K-major like every other operand; read in place it is [key][d] =
+    // MN-major (b_major, instruction-descriptor bit 16): rows = K (keys) 128 B apart, 8-row groups SBO = 1024 B apart, the 64 d of
+    // a row are one 128-B swizzle span, a K = 16 step advances 2048 B (cute/atom/mma_traits_sm100.hpp, canonical Major-MN B128)
+    const uint32_t idesc_o = umma_idesc_f16(128, 64, 1) | (p.vmajor ? (1u << 16) : 0u);
     const uint64_t dconst = (1ull << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
     const uint32_t q16 = (smem_u32(sQ) & 0x3FFFF) >> 4, k16 = (smem_u32(sK) & 0x3FFFF) >> 4;
     const uint32_t v16 = (smem_u32(sV) & 0x3FFFF) >> 4, p16 = (smem_u32(sP) & 0x3FFFF) >> 4;
@@ -165,10 +172,11 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tc_kernel(const __g
         for (int kb = 0; kb < nkb; ++kb) {
           const uint64_t ad = dconst | (p16 + kb * (16384 >> 4));
           const uint64_t bd = dconst | (v16 + kb * (8192 >> 4));
+          const uint32_t bstep = p.vmajor ? (2048 >> 4) : 2;        // per K = 16: 16 key rows (MN-major) or 32 B along the row (K-major)
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             if (kb == 0 && k == 0) umma_f16_c<false>(tmem_base + kOCol, ad, bd, idesc_o);
-            else umma_f16_c<true>(tmem_base + kOCol, ad + 2 * k, bd + 2 * k, idesc_o);
+            else umma_f16_c<true>(tmem_base + kOCol, ad + 2 * k, bd + bstep * k, idesc_o);
           }
         }
         umma_commit(bar_o);
@@ -203,9 +211,14 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tc_kernel(const __g
         uint32_t v[16];
         tmem_ld16(t_row + c0, v);
         tmem_ld_wait();
+        if (__all_sync(0xffffffffu, c0 >= lo && c0 + 15 <= lim)) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (c0 + j >= lo && c0 + j <= lim) m = fmaxf(m, __uint_as_float(v[j]));
+          for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j >= lo && c0 + j <= lim) m = fmaxf(m, __uint_as_float(v[j]));
+        }
       }
       sRed[half * 128 + row] = m;
       named_bar_sync(1, 256);                     // the two column halves of every row exchange their maxima
@@ -224,12 +237,23 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tc_kernel(const __g
         tmem_ld16(t_row + c0, v);
         tmem_ld_wait();
         float e[16];
+        // chunks that lie inside every row's own key range (all but the edges of an image's keys) skip the per-element mask:
+        // the pass is bound by instruction issue next to the MUFU, and the mask is three of its ~7 instructions per element
+        const bool inner = __all_sync(0xffffffffu, c0 >= lo && c0 + 15 <= lim);
+        if (inner) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float x;
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(x) : "f"(fmaf(__uint_as_float(v[j]), kScale, -mc)));
-          e[j] = (c0 + j >= lo && c0 + j <= lim) ? x : 0.f;
-          sum += e[j];
+          for (int j = 0; j < 16; ++j) {
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[j]) : "f"(fmaf(__uint_as_float(v[j]), kScale, -mc)));
+            sum += e[j];
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float x;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(x) : "f"(fmaf(__uint_as_float(v[j]), kScale, -mc)));
+            e[j] = (c0 + j >= lo && c0 + j <= lim) ? x : 0.f;
+            sum += e[j];
+          }
         }
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
@@ -336,7 +360,18 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tc_kernel(const __g
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     __syncwarp();
     mbar_wait(bar_v, 0);
-    float o0 = 0.f, o1 = 0.f;                     // output dims lane and lane + 32
+    float o0 = 0.f, o1 = 0.f;                     // output dims: (lane, lane + 32) from V^T, (2 lane, 2 lane + 1) from V in place
+    if (p.vmajor) {
+      for (int j = 0; j < Lt; ++j) {              // V row j: [64 d] = 128 B, 16-B chunk c at slot c ^ (j & 7); this lane's two d's = one word
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(sV + (j >> 6) * 8192 + (j & 63) * 128 + ((((lane >> 2) ^ (j & 7))) << 4) + (lane & 3) * 4);
+        const float pj = sPt[j];
+        o0 = fmaf(pj, __uint_as_float(w << 16), o0);
+        o1 = fmaf(pj, __uint_as_float(w & 0xFFFF0000u), o1);
+      }
+      const float inv = 1.0f / sum;
+      __nv_bfloat162 r = __floats2bfloat162_rn(o0 * inv, o1 * inv);
+      *reinterpret_cast<__nv_bfloat162*>(p.ctx + (static_cast<long long>(row0) + qi) * p.W + h * 64 + 2 * lane) = r;
+    } else {
     for (int kb = 0; kb < nkb; ++kb) {
       const uint8_t* v0 = sV + kb * 8192 + lane * 128;
       const uint8_t* v1 = v0 + 32 * 128;
@@ -360,6 +395,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tc_kernel(const __g
     __nv_bfloat16* out = p.ctx + (static_cast<long long>(row0) + qi) * p.W + h * 64;
     out[lane] = __float2bfloat16_rn(o0 * inv);
     out[lane + 32] = __float2bfloat16_rn(o1 * inv);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -413,6 +449,8 @@ int attention_tc_launch(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, __nv_bfloa
   PFN_encodeTiled enc = get_encode_tiled();
   CC_REQUIRE(enc != nullptr, "attention_tc: cuTensorMapEncodeTiled unavailable");
   AttnParams p{};
+  static const int vt_env = getenv("CC_ATTN_VT") ? atoi(getenv("CC_ATTN_VT")) : 0;
+  p.vmajor = vt_env ? 0 : 1;
   p.qkv = qkv; p.ctx = ctx; p.tail = (G == 1 && L > 128 && (L & 127) == 1) ? 1 : 0; p.B = B; p.L = L; p.Lk = Lk; p.H = H; p.W = W; p.causal = causal; p.G = G;
   p.tmem_cols = 32;
   while (p.tmem_cols < Lk + 64) p.tmem_cols <<= 1;
@@ -434,8 +472,10 @@ int attention_tc_launch(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, __nv_bfloa
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     CC_REQUIRE(r == CUDA_SUCCESS, "attention_tc: tensor map (Vt) failed: %d", int(r));
   }
-  vt_kernel<<<dim3(NG * H, nkb), 256, 0, st>>>(qkv, vt_ws, G * L, static_cast<long long>(B) * L, Lk, H, W);
-  CC_CHECK_CUDA(cudaGetLastError());
+  if (!p.vmajor) {
+    vt_kernel<<<dim3(NG * H, nkb), 256, 0, st>>>(qkv, vt_ws, G * L, static_cast<long long>(B) * L, Lk, H, W);
+    CC_CHECK_CUDA(cudaGetLastError());
+  }
   const int smem = 1024 + 128 * 128 + Lk * 128 + nkb * 8192 + nkb * 16384 + 64 + (512 + kMaxLk) * 4;
   static bool attr_set = false;
   if (!attr_set) {

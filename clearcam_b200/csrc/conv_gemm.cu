@@ -947,6 +947,7 @@ budget_again:
   const int bres_bytes = BN * p.BK * 2 * p.num_taps * p.chunks_per_tap;
   // resident weights up to 128 KB (a 1x1 conv 256 -> 256): with the halved staging of level 1 four activation stages still fit
   static const int bres_kb_env = getenv("CC_BRES_KB") ? atoi(getenv("CC_BRES_KB")) : 128;
+  static const int bres_min_stages = getenv("CC_BRES_MIN_STAGES") ? atoi(getenv("CC_BRES_MIN_STAGES")) : 4;
   p.b_res = (bres_env && p.n_blocks == 1 && bres_bytes <= bres_kb_env * 1024) ? 1 : 0;
   p.halo_stages = 2;
   if (p.halo) {
@@ -991,7 +992,7 @@ budget_again:
     }
     p.halo_stages = hs;
     L->smem_bytes = fixed + wbytes + hs * p.halo_bytes + stage_pad(wbytes + hs * p.halo_bytes);
-  } else if (p.b_res && (kMaxSmem - fixed - bres_bytes) / (kTileM * p.BK * 2) >= 4) {
+  } else if (p.b_res && (kMaxSmem - fixed - bres_bytes) / (kTileM * p.BK * 2) >= bres_min_stages) {
     const int a_bytes = kTileM * p.BK * 2;
     S = (kMaxSmem - fixed - bres_bytes) / a_bytes;
     if (S > 8) S = 8;

@@ -16,6 +16,9 @@ shapes = [  # N,H,W,Cin,Cout,k,s
     (32, 40, 40, 128, 128, 3, 1),
     (32, 80, 80, 512, 512, 1, 1),
     (32, 20, 20, 256, 256, 1, 1),
+    (32, 320, 320, 64, 128, 3, 2),      # 11: model.1
+    (32, 160, 160, 256, 256, 1, 1),     # 12 (= 5): model.2.cv4
+    (32, 160, 160, 128, 128, 1, 1),     # 13 (= 0): model.2.cv1
 ]
 sel = [int(a) for a in sys.argv[2:]] or range(len(shapes))
 for si in sel:
