@@ -306,9 +306,9 @@ class Ctx:
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
             self.dist = dist
             # the seeded synthetic weights are generated on the CPU by every rank: share the host cores
-            torch.set_num_threads(max(1, min(16, (os.cpu_count() or 8) // self.world)))
+            torch.set_num_threads(max(1, min(16, usable_cpus() // self.world)))
         else:
-            torch.set_num_threads(min(16, os.cpu_count() or 8))
+            torch.set_num_threads(min(16, usable_cpus()))
         self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def barrier(self):

@@ -29,7 +29,9 @@ struct AttnParams {
   const __nv_bfloat16* qkv;
   __nv_bfloat16* ctx;
   int B, L, Lk, H, W, causal;
+  int nq;          // Q buffers (2 where shared memory allows: both query blocks of a 257-token sequence are loaded up front)
   int vmajor;      // 1: V is read in place from the QKV buffer ([key][64 d] tiles = an MN-major B operand); 0: from the V^T pre-pass
+  unsigned long long* trace;   // diagnostic (CC_ATTN_TRACE=1): SM-cycle stamps of CTA 0, see attention_tc_launch
   int tail;        // 1: one image per CTA and L = 128 n + 1 -> the last token runs on CUDA cores (warp 9)
   int G;           // images per CTA (packed sequence of G*L tokens, Lk = ceil(G*L / 64) * 64 key columns)
   int tmem_cols;   // power of two >= Lk + 64
@@ -65,28 +67,32 @@ __global__ void __launch_bounds__(256) vt_kernel(const __nv_bfloat16* __restrict
 // warps: 0 = control (TMA + MMA issue), 1..8 = softmax (two warps per TMEM lane quarter, each taking every other 16-column
 // chunk of a row), 9 = tail row on CUDA cores (sequences of 128 n + 1 tokens, i.e. ViT-L/14's 257: the last token would
 // otherwise cost a whole 128-row block of MMA + softmax work for one row)
-static constexpr int kAttnThreads = 320;
+static constexpr int kParts = 2;                       // softmax warps per TMEM lane quarter (each takes every kParts-th 16-column chunk)
+static constexpr int kSoftWarps = 4 * kParts;
+static constexpr int kAttnThreads = 32 * (2 + kSoftWarps);   // control + softmax + tail-row warp
 __global__ void __launch_bounds__(kAttnThreads, 1) attention_tc_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[13] = clock64();   // kernel entry
   const int nkb = p.Lk >> 6;                       // 64-key blocks
-  uint8_t* sQ = smem;                              // [128][128 B]
-  uint8_t* sK = sQ + 128 * 128;                    // [Lk][128 B]
+  uint8_t* sQ = smem;                              // nq x [128][128 B]
+  uint8_t* sK = sQ + p.nq * 128 * 128;             // [Lk][128 B]
   uint8_t* sV = sK + p.Lk * 128;                   // nkb x [64 d][128 B]
   uint8_t* sP = sV + nkb * 8192;                   // nkb x [128 rows][128 B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + nkb * 16384);
   uint64_t* bar_k = bars;        // K landed
   uint64_t* bar_v = bars + 1;    // V^T landed
-  uint64_t* bar_q = bars + 2;    // Q block landed            (phase per q-block)
+  uint64_t* bar_q = bars + 2;    // Q block landed, buffer 0 (buffer 1: bars + 7)
   uint64_t* bar_s = bars + 3;    // S = QK^T complete
   uint64_t* bar_p = bars + 4;    // P written (8 arrivals: one per softmax warp)
   uint64_t* bar_o = bars + 5;    // O = PV complete
   uint64_t* bar_oe = bars + 6;   // O read back (8 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
-  float* sRed = reinterpret_cast<float*>(bars + 8);   // [2][128] partial row maxima of the two column halves
-  float* sSum = sRed + 256;                            // [2][128] partial row sums
-  float* sPt = sSum + 256;                             // [kMaxLk] tail row probabilities
+  uint64_t* bar_q1 = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* sRed = reinterpret_cast<float*>(bars + 10);   // [kParts][128] partial row maxima of the column parts
+  float* sSum = sRed + kParts * 128;                   // [kParts][128] partial row sums
+  float* sPt = sSum + kParts * 128;                             // [kMaxLk] tail row probabilities
 
   const int bh = blockIdx.x, grp = bh / p.H, h = bh % p.H;
   const int nimg = (p.B - grp * p.G) < p.G ? (p.B - grp * p.G) : p.G;   // images in this group (the last one may be short)
@@ -100,8 +106,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tc_kernel(const __g
     if (lane == 0) {
       tma_prefetch_desc(&p.tmQK);
       tma_prefetch_desc(&p.tmVt);
-      mbar_init(bar_k, 1); mbar_init(bar_v, 1); mbar_init(bar_q, 1); mbar_init(bar_s, 1);
-      mbar_init(bar_p, 8); mbar_init(bar_o, 1); mbar_init(bar_oe, 8);   // one arrival per softmax warp
+      mbar_init(bar_k, 1); mbar_init(bar_v, 1); mbar_init(bar_q, 1); mbar_init(bar_q1, 1); mbar_init(bar_s, 1);
+      mbar_init(bar_p, kSoftWarps); mbar_init(bar_o, 1); mbar_init(bar_oe, kSoftWarps);   // one arrival per softmax warp
       fence_mbar_init();
     }
     __syncwarp();
@@ -112,21 +118,29 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tc_kernel(const __g
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const bool tr = p.trace != nullptr && blockIdx.x == 0;
+  if (tr && threadIdx.x == 0) p.trace[0] = clock64();          // set-up done
 
   if (warp == 0) {
     // ===================== control warp: TMA loads + MMA issue (one elected lane) =====================
     if (lane == 0) {
+      // order = order of use: Q(0) and K feed the first S, V is needed only by the first P.V (the in-kernel timeline — CC_ATTN_TRACE —
+      // showed the first S waiting ~9000 cycles for all 96 KB, and the second query block waiting for its Q to be fetched)
+      auto load_q = [&](int qb) {
+        uint64_t* bq = (qb & 1) && p.nq == 2 ? bar_q1 : bar_q;
+        uint8_t* dst = sQ + ((qb & 1) && p.nq == 2 ? 128 * 128 : 0);
+        mbar_arrive_expect_tx(bq, 128 * 128);
+        tma_load_2d(dst, &p.tmQK, bq, h * 64, row0 + 128 * qb);
+        tma_load_2d(dst + 8192, &p.tmQK, bq, h * 64, row0 + 128 * qb + 64);
+      };
+      if (nqb > 0) load_q(0);
       mbar_arrive_expect_tx(bar_k, p.Lk * 128);
       for (int j = 0; j < nkb; ++j) tma_load_2d(sK + j * 8192, &p.tmQK, bar_k, p.W + h * 64, row0 + 64 * j);
+      if (nqb > 1 && p.nq == 2) load_q(1);
       mbar_arrive_expect_tx(bar_v, nkb * 8192);
       for (int j = 0; j < nkb; ++j) {
         if (p.vmajor) tma_load_2d(sV + j * 8192, &p.tmQK, bar_v, 2 * p.W + h * 64, row0 + 64 * j);   // V rows as they are: [key][64 d]
         else tma_load_2d(sV + j * 8192, &p.tmVt, bar_v, 64 * j, bh * 64);
-      }
-      if (nqb > 0) {
-        mbar_arrive_expect_tx(bar_q, 128 * 128);
-        tma_load_2d(sQ, &p.tmQK, bar_q, h * 64, row0);
-        tma_load_2d(sQ + 8192, &p.tmQK, bar_q, h * 64, row0 + 64);
       }
     }
     __syncwarp();
@@ -138,13 +152,16 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tc_kernel(const __g
     // a row are one 128-B swizzle span, a K = 16 step advances 2048 B (cute/atom/mma_traits_sm100.hpp, canonical Major-MN B128)
     const uint32_t idesc_o = umma_idesc_f16(128, 64, 1) | (p.vmajor ? (1u << 16) : 0u);
     const uint64_t dconst = (1ull << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-    const uint32_t q16 = (smem_u32(sQ) & 0x3FFFF) >> 4, k16 = (smem_u32(sK) & 0x3FFFF) >> 4;
+    const uint32_t q16_0 = (smem_u32(sQ) & 0x3FFFF) >> 4, k16 = (smem_u32(sK) & 0x3FFFF) >> 4;
     const uint32_t v16 = (smem_u32(sV) & 0x3FFFF) >> 4, p16 = (smem_u32(sP) & 0x3FFFF) >> 4;
     mbar_wait(bar_k, 0);
+    if (tr && lane == 0) p.trace[1] = clock64();              // K landed
     for (int qb = 0; qb < nqb; ++qb) {
       const uint32_t ph = qb & 1;
-      mbar_wait(bar_q, ph);
+      const bool qodd = (qb & 1) && p.nq == 2;
+      mbar_wait(qodd ? bar_q1 : bar_q, p.nq == 2 ? ((qb >> 1) & 1) : ph);
       tc_fence_after();
+      const uint32_t q16 = q16_0 + (qodd ? ((128 * 128) >> 4) : 0);
       if (elect_one()) {
         for (int c = 0; c < nch; ++c) {
           const uint64_t bd = dconst | (k16 + ((c * chN * 128) >> 4));
@@ -159,10 +176,13 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tc_kernel(const __g
       __syncwarp();
       mbar_wait(bar_p, ph);          // P ready (=> S fully read, first MMA long done: Q buffer is free)
       tc_fence_after();
-      if (qb + 1 < nqb && lane == 0) {
-        mbar_arrive_expect_tx(bar_q, 128 * 128);
-        tma_load_2d(sQ, &p.tmQK, bar_q, h * 64, row0 + 128 * (qb + 1));
-        tma_load_2d(sQ + 8192, &p.tmQK, bar_q, h * 64, row0 + 128 * (qb + 1) + 64);
+      if (qb + p.nq < nqb && lane == 0) {        // the buffer S(qb) read is free: fetch the query block that uses it next
+        const int nx = qb + p.nq;
+        uint64_t* bq = (nx & 1) && p.nq == 2 ? bar_q1 : bar_q;
+        uint8_t* dst = sQ + ((nx & 1) && p.nq == 2 ? 128 * 128 : 0);
+        mbar_arrive_expect_tx(bq, 128 * 128);
+        tma_load_2d(dst, &p.tmQK, bq, h * 64, row0 + 128 * nx);
+        tma_load_2d(dst + 8192, &p.tmQK, bq, h * 64, row0 + 128 * nx + 64);
       }
       __syncwarp();
       if (qb == 0) mbar_wait(bar_v, 0);
@@ -183,10 +203,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tc_kernel(const __g
       }
       __syncwarp();
     }
-  } else if (warp <= 8) {
+  } else if (warp <= kSoftWarps) {
     // ===================== softmax / epilogue warps (thread pair == query row) =====================
     const int quarter = warp & 3;
-    const int half = (warp - 1) >> 2;             // which 16-column chunks of a row this warp handles (chunk parity)
+    const int half = (warp - 1) >> 2;             // which 16-column chunks of a row this warp handles (chunk index mod kParts)
     const int row = quarter * 32 + lane;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const float kScale = 0.125f * 1.4426950408889634f;   // 1/sqrt(64) * log2(e)
@@ -206,8 +226,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tc_kernel(const __g
       const int w_hi = __reduce_max_sync(0xffffffffu, lim);
       mbar_wait(bar_s, ph);
       tc_fence_after();
+      const bool trs = tr && warp == 1 && lane == 0 && qb < 2;
+      if (trs) p.trace[2 + 5 * qb] = clock64();                 // S complete
       float m = -INFINITY;
-      for (int c0 = w_lo + 16 * half; c0 <= w_hi; c0 += 32) {
+      for (int c0 = w_lo + 16 * half; c0 <= w_hi; c0 += 16 * kParts) {
         uint32_t v[16];
         tmem_ld16(t_row + c0, v);
         tmem_ld_wait();
@@ -221,11 +243,13 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tc_kernel(const __g
         }
       }
       sRed[half * 128 + row] = m;
-      named_bar_sync(1, 256);                     // the two column halves of every row exchange their maxima
-      m = fmaxf(m, sRed[(half ^ 1) * 128 + row]);
+      named_bar_sync(1, 32 * kSoftWarps);         // the column parts of every row exchange their maxima
+#pragma unroll
+      for (int q = 0; q < kParts; ++q) m = fmaxf(m, sRed[q * 128 + row]);
+      if (trs) p.trace[3 + 5 * qb] = clock64();                 // row maxima known
       const float mc = m * kScale;
       float sum = 0.f;
-      for (int c0 = 16 * half; c0 < p.Lk; c0 += 32) {
+      for (int c0 = 16 * half; c0 < p.Lk; c0 += 16 * kParts) {
         uint8_t* blk = sP + (c0 >> 6) * 16384 + row * 128;
         const uint32_t i0 = (c0 & 63) >> 3;
         if (c0 < w_lo || c0 > w_hi) {            // keys of images no row of this warp belongs to: P = 0, no TMEM read, no exponentials
@@ -266,6 +290,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tc_kernel(const __g
           *reinterpret_cast<uint4*>(blk + (((i0 + q) ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
+      if (trs) p.trace[4 + 5 * qb] = clock64();                 // this warp's P written
       sSum[half * 128 + row] = sum;               // read by the partner after bar_o (ordered through bar_p -> MMA -> bar_o)
       fence_proxy_async_smem();
       tc_fence_before();
@@ -274,12 +299,17 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tc_kernel(const __g
       // ---- O -> ctx: each warp of the pair normalises and stores 32 of the 64 output columns
       mbar_wait(bar_o, ph);
       tc_fence_after();
-      const float inv = 1.0f / (sum + sSum[(half ^ 1) * 128 + row]);
-      __nv_bfloat16* out = p.ctx + (static_cast<long long>(row0) + qi) * p.W + h * 64 + 32 * half;
+      if (trs) p.trace[5 + 5 * qb] = clock64();                 // O complete
+      float tot = 0.f;
 #pragma unroll
-      for (int c0 = 0; c0 < 32; c0 += 16) {
+      for (int q = 0; q < kParts; ++q) tot += sSum[q * 128 + row];      // (own part included: fixed summation order for all warps of a row)
+      const float inv = 1.0f / tot;
+      constexpr int kOC = 64 / kParts;            // output columns per warp (16 with four parts)
+      __nv_bfloat16* out = p.ctx + (static_cast<long long>(row0) + qi) * p.W + h * 64 + kOC * half;
+#pragma unroll
+      for (int c0 = 0; c0 < kOC; c0 += 16) {
         uint32_t v[16];
-        tmem_ld16(t_row + kOCol + 32 * half + c0, v);
+        tmem_ld16(t_row + kOCol + kOC * half + c0, v);
         tmem_ld_wait();
         if (qi < Lt) {
 #pragma unroll
@@ -295,6 +325,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tc_kernel(const __g
           }
         }
       }
+      if (trs) p.trace[6 + 5 * qb] = clock64();                 // O stored
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_oe);
@@ -399,6 +430,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_tc_kernel(const __g
   }
   tc_fence_before();
   __syncthreads();
+  if (tr && threadIdx.x == 0) p.trace[12] = clock64();         // all roles done
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
@@ -476,11 +508,30 @@ int attention_tc_launch(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, __nv_bfloa
     vt_kernel<<<dim3(NG * H, nkb), 256, 0, st>>>(qkv, vt_ws, G * L, static_cast<long long>(B) * L, Lk, H, W);
     CC_CHECK_CUDA(cudaGetLastError());
   }
-  const int smem = 1024 + 128 * 128 + Lk * 128 + nkb * 8192 + nkb * 16384 + 64 + (512 + kMaxLk) * 4;
+  p.nq = (1024 + 2 * 128 * 128 + Lk * 128 + nkb * 8192 + nkb * 16384 + 80 + (2 * kParts * 128 + kMaxLk) * 4 <= 227 * 1024) ? 2 : 1;
+  const int smem = 1024 + p.nq * 128 * 128 + Lk * 128 + nkb * 8192 + nkb * 16384 + 80 + (2 * kParts * 128 + kMaxLk) * 4;
   static bool attr_set = false;
   if (!attr_set) {
     CC_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
+  }
+  static const int trace_env = getenv("CC_ATTN_TRACE") ? atoi(getenv("CC_ATTN_TRACE")) : 0;
+  static int traced = 0;
+  if (trace_env && traced < 2 && L > 128) {       // diagnostic only: synchronises and prints the timeline of CTA 0 (SM cycles)
+    ++traced;
+    unsigned long long* d = nullptr;
+    cudaMalloc(&d, 16 * 8);
+    cudaMemsetAsync(d, 0, 16 * 8, st);
+    p.trace = d;
+    attention_tc_kernel<<<NG * H, kAttnThreads, smem, st>>>(p);
+    unsigned long long h[16];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    const unsigned long long t0 = h[13];
+    fprintf(stderr, "attention_tc CTA 0 timeline (SM cycles after kernel entry; B=%d L=%d Lk=%d G=%d): setup %llu | K landed %llu | qb0: S %llu max %llu P %llu O %llu stored %llu | qb1: S %llu max %llu P %llu O %llu stored %llu | done %llu\n",
+            B, L, Lk, G, h[0] - t0, h[1] - t0, h[2] - t0, h[3] - t0, h[4] - t0, h[5] - t0, h[6] - t0, h[7] - t0, h[8] - t0, h[9] - t0, h[10] - t0, h[11] - t0, h[12] - t0);
+    return CC_OK;
   }
   attention_tc_kernel<<<NG * H, kAttnThreads, smem, st>>>(p);
   CC_CHECK_CUDA(cudaGetLastError());
