@@ -395,6 +395,16 @@ def yolo_section(cx, with_cpu):
             d = by.setdefault(r["kind"], {"ms": 0.0, "flops": 0.0, "n": 0})
             d["ms"] += r["ms"]; d["flops"] += r["flops"]; d["n"] += 1
         gm = by.get("conv_gemm", {"ms": 1e-9, "flops": 0.0, "n": 0})
+        # the memory-bound kernels: algorithmic bytes (inputs once + outputs once) / event-bracketed time, against the measured copy
+        hbm = {}
+        for r in prof:
+            if r["kind"] != "conv_gemm" and r.get("bytes", 0) > 0:
+                d = hbm.setdefault(r["kind"], {"ms": 0.0, "bytes": 0.0, "launches": 0})
+                d["ms"] += r["ms"]; d["bytes"] += r["bytes"]; d["launches"] += 1
+        for d in hbm.values():
+            d["GB/s"] = d["bytes"] / (d["ms"] / 1000.0) / 1e9
+            d["frac_of_hbm"] = d["GB/s"] / pk["hbm"]
+            d["ms"] = round(d["ms"], 4); d["bytes"] = int(d["bytes"])
         achieved = gm["flops"] / (gm["ms"] / 1000.0) / 1e12
         total_prof_ms = sum(d["ms"] for d in by.values())
         try:
@@ -421,7 +431,8 @@ def yolo_section(cx, with_cpu):
                 "share_of_step_events": gm["ms"] / total_prof_ms,
                 "whole_step_tflops": B * GFLOP_PER_FRAME / 1000.0 / (ms_total / K / 1000.0),
                 "whole_step_frac": B * GFLOP_PER_FRAME / 1000.0 / (ms_total / K / 1000.0) / pk["tflops_sustained"],
-                "per_kind_ms_events": {k: round(v["ms"], 4) for k, v in by.items()}}
+                "per_kind_ms_events": {k: round(v["ms"], 4) for k, v in by.items()},
+                "memory_bound_kernels": {"peak": pk["hbm"], "unit": "GB/s", "peak_src": pk["src"] + " (copy)", "kernels": hbm}}
         cpu = None
         if with_cpu:                   # rank 0 at N=1 only: the other ranks must not sit in a barrier
             cpu = cpu_pool("yolo", P, steps=16, warmup=2)              # ~64 frames, ~10 s: the same order as the reference arm at the driver's K

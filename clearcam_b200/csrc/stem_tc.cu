@@ -93,7 +93,9 @@ __global__ void __launch_bounds__(128, 6) stem_tc_kernel(const __grid_constant__
           if (ix < 0 || ix >= p.W) continue;
           const uint8_t* px = rowp + ix * 3;
 #pragma unroll
-          for (int c = 0; c < 3; ++c) v[(r * 3 + s) * 3 + c] = static_cast<float>(__ldg(px + 2 - c));
+          // byte -> float without the conversion unit (I2F shares the 16-lane/clk XU pipe with the 64 MUFU.TANH of this thread's
+          // row; ncu had the kernel at 53 % XU): 0x4B000000 | b is the float 2^23 + b exactly, one subtraction leaves b
+          for (int c = 0; c < 3; ++c) v[(r * 3 + s) * 3 + c] = __uint_as_float(0x4B000000u | __ldg(px + 2 - c)) - 8388608.0f;
         }
       }
     }

@@ -863,6 +863,20 @@ static int plan_run(YoloPlan& P, const void* d_frames, float* d_out, float* d_ra
   return CC_OK;
 }
 
+// algorithmic HBM bytes of a memory-bound op (inputs once + outputs once), for the achieved-GB/s figures of the bench line
+static double op_bytes(const Op& op) {
+  auto sl = [](const TSlice& t) { return double(t.N) * t.H * t.W * t.C * (t.f32 ? 4 : 2); };
+  switch (op.kind) {
+    case Op::AVGPAD: case Op::AVGMAX: case Op::MAXPOOL5: case Op::UPSAMPLE: return sl(op.s_in) + sl(op.s_out);
+    case Op::SPP3: return 4.0 * op.s_in.N * op.s_in.H * op.s_in.W * op.s_out.C * 2;
+    case Op::CBFUSE: { double b = sl(op.cbf.last) + sl(op.cbf.out); for (int k = 0; k < op.cbf.nsrc; ++k) b += sl(op.cbf.src[k]); return b; }
+    case Op::STEM_TC: return double(op.stem_tc.B) * op.stem_tc.H * op.stem_tc.W * 3 + double(op.stem_tc.Mrows) * op.stem_tc.Cout * 2;
+    case Op::LETTERBOX: return double(op.lb.B) * (double(op.lb.Hin) * op.lb.Win + double(op.lb.Hout) * op.lb.Wout) * 3 * (op.lb.is_f32 ? 4 : 1);
+    case Op::DECODE: return double(op.dec.B) * op.dec.A * ((64 + 80) * 4 + 6 * 4);
+    default: return 0.0;
+  }
+}
+
 static const char* op_kind_name(Op::Kind k) {
   switch (k) {
     case Op::GEMM: return "conv_gemm"; case Op::DIRECT: return "conv_direct"; case Op::AVGPAD: return "avgpool2_pad";
@@ -1135,7 +1149,7 @@ int cc_yolo_profile(cc_yolo* h, const void* d_frames, int is_f32, int B, int Hf,
       cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
       if (ms) ms[i] = t;
       if (flops) flops[i] = P->ops[i].kind == Op::GEMM ? P->ops[i].gemm.flops : P->ops[i].flops;
-      if (bytes) bytes[i] = P->ops[i].kind == Op::GEMM ? P->ops[i].gemm.bytes : 0.0;
+      if (bytes) bytes[i] = P->ops[i].kind == Op::GEMM ? P->ops[i].gemm.bytes : op_bytes(P->ops[i]);
       if (kinds) kinds[i] = op_kind_name(P->ops[i].kind);
       if (names) names[i] = P->ops[i].name.c_str();
     }
