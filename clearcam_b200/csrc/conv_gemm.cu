@@ -129,7 +129,7 @@ __device__ __forceinline__ void mma_issuer(const GemmParams& p, uint8_t* sA, uin
     const uint64_t lay = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);
     const uint64_t dconst = (1ull << 16) | (1ull << 46) | (lay << 61);
     const uint64_t d_tile = dconst | (static_cast<uint64_t>((8u * row_bytes) >> 4) << 32);    // dense 128-row tiles
-    const uint64_t d_halo = dconst | (static_cast<uint64_t>((16u * row_bytes) >> 4) << 32);   // halo views: 16-px row pitch
+    const uint64_t d_halo = dconst | (static_cast<uint64_t>((static_cast<uint32_t>(p.halo_pitch) * row_bytes) >> 4) << 32);   // halo views: 8-px groups one halo row apart
     const uint32_t sA16 = (smem_u32(sA) & 0x3FFFF) >> 4, sB16 = (smem_u32(sB) & 0x3FFFF) >> 4;
     const uint32_t a16 = a_bytes >> 4, b16 = b_bytes >> 4, h16 = p.halo_bytes >> 4;
     const Sched sc = make_sched(p);
@@ -146,7 +146,7 @@ __device__ __forceinline__ void mma_issuer(const GemmParams& p, uint8_t* sA, uin
     if (p.halo) {
       int sa = 0;
       uint32_t pa = 0;
-      const uint32_t rstep16 = ((16u << p.lTN) * row_bytes) >> 4;  // one halo row block (TN images x 16 px), in 16-B units
+      const uint32_t rstep16 = ((static_cast<uint32_t>(p.halo_pitch) << p.lTN) * row_bytes) >> 4;  // one halo row block (TN images x pitch px), in 16-B units
       const uint32_t sstep16 = row_bytes >> 4;                      // one pixel
       const uint32_t btap16 = cpt * b16;                            // resident weights: descriptor step between taps
       for (int slot = sc.first; slot < sc.limit; slot += sc.step) {
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             mbar_wait(&aempty_bar[sa], pa ^ 1);
             if (p.dbg & 4) mbar_arrive(&afull_bar[sa]);
             else {
-              mbar_arrive_expect_tx(&afull_bar[sa], p.halo_bytes);
+              mbar_arrive_expect_tx(&afull_bar[sa], p.halo_tx);
               tma_load_5d(sA + sa * p.halo_bytes, &p.tmA, &afull_bar[sa], ch * p.BK, w0 - 1, n0, h0 - 1, 0);
             }
             if (++sa == p.halo_stages) { sa = 0; pa ^= 1; }
@@ -790,7 +790,16 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
       if (eff > be) { be = eff; p.lTH = lh; p.lTN = 4 - lh; }
     }
     p.lTW = 3;
-    p.halo_bytes = p.BK * 16 * (1 << p.lTN) * ((1 << p.lTH) + 2) * 2;
+    // Halo row pitch in shared memory.  The taps read pixels w0-1 .. w0+8 of a row: 10 pixels.  Round 1 loaded 16 (a
+    // power-of-two pitch keeps every 8-pixel group on a swizzle-atom boundary), i.e. 2.25x the tile's own bytes from L2 per
+    // chunk; the small-channel 3x3 layers move ~5 TB/s between L2 and the SMs, which is where that fabric saturates, with
+    // both pipes idle.  The swizzle XOR is a function of ABSOLUTE shared-memory address bits for TMA writes and UMMA reads
+    // alike (the tap views already start 128 B off an atom boundary), so a 10-pixel pitch (stride between 8-row groups =
+    // 10 rows, not a multiple of the atom) reads back what was written: 1.41x instead of 2.25x.
+    static const int hpitch_env = getenv("CC_HALO_PITCH") ? atoi(getenv("CC_HALO_PITCH")) : 10;
+    p.halo_pitch = hpitch_env == 16 ? 16 : 10;
+    p.halo_tx = p.BK * p.halo_pitch * (1 << p.lTN) * ((1 << p.lTH) + 2) * 2;
+    p.halo_bytes = (p.halo_tx + 1023) & ~1023;                  // stage stride: buffers stay 1024-B aligned
   }
   const int TW = 1 << p.lTW, TH = 1 << p.lTH, TN = 1 << p.lTN;
   p.tiles_w = (Wout + TW - 1) / TW;
@@ -825,10 +834,10 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
     cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
     const cuuint64_t px = cuuint64_t(d.in_cs) * 2;  // bytes per pixel
     if (p.halo) {
-      // (C, W, N, H): the box [64 ch][16 px][TN images][TH+2 rows] lands in smem as [row][image][pixel][128 B]
+      // (C, W, N, H): the box [64 ch][pitch px][TN images][TH+2 rows] lands in smem as [row][image][pixel][128 B]
       dims[0] = d.Cin; dims[1] = d.Win; dims[2] = d.N; dims[3] = d.Hin; dims[4] = 1;
       strides[0] = px; strides[1] = px * d.Win * d.Hin; strides[2] = px * d.Win; strides[3] = px * d.Win * d.Hin * d.N;
-      box[0] = p.BK; box[1] = 16; box[2] = TN; box[3] = TH + 2; box[4] = 1;
+      box[0] = p.BK; box[1] = p.halo_pitch; box[2] = TN; box[3] = TH + 2; box[4] = 1;
     } else if (!p.s2) {
       dims[0] = d.Cin; dims[1] = d.Win; dims[2] = d.Hin; dims[3] = d.N; dims[4] = 1;
       strides[0] = px; strides[1] = px * d.Win; strides[2] = px * d.Win * d.Hin; strides[3] = px * d.Win * d.Hin * d.N;

@@ -44,6 +44,7 @@ struct GemmParams {
   // the nine taps are shifted shared-memory descriptor views of it
   int32_t halo, halo_bytes, halo_bo;  // enabled / bytes per halo stage / descriptor base_offset mode
   int32_t halo_stages;                // 2..4 halo buffers in flight
+  int32_t halo_pitch, halo_tx;        // pixels per halo row in shared memory (10: exactly the 8 + 2 the taps read; 16: round-1 layout) / bytes one halo load transfers
   int32_t tma_store;                  // epilogue stores through TMA from swizzled staging (one buffer per epilogue group)
   int32_t b_res;                      // weights of the (single) N block stay resident in smem for the whole kernel
   int32_t res_tma;                    // in-place residual is prefetched into the staging buffer by TMA (through tmC)
