@@ -745,7 +745,8 @@ int conv_gemm_build(const ConvDesc& d, int num_sms, GemmLaunch* L) {
         const double tiles = double(mt) * (d.Cout / bn);
         const double rounds = ceil(tiles / num_sms);
         const double mma = nkb * (2.0 * bn > 160 ? 2.0 * bn : 160.0) * bk / 64.0;
-        const double a_bytes = (d.k == 3 && d.stride == 1 && bk >= 32) ? 128.0 * bk * 2 * 2.25 / 9 : 128.0 * bk * 2;  // halo re-use
+        static const double halo_cost = getenv("CC_HALO_COST") ? atof(getenv("CC_HALO_COST")) : 2.25;
+        const double a_bytes = (d.k == 3 && d.stride == 1 && bk >= 32) ? 128.0 * bk * 2 * halo_cost / 9 : 128.0 * bk * 2;  // halo re-use
         const double load = nkb * (a_bytes + bn * bk * 2.0) / 40.0;
         const double epi = bn * 10.0 + 600.0;
         const double tile = (mma > load ? mma : load);
@@ -891,17 +892,27 @@ budget_again:
   p.stg_nbuf = nbuf;
   // column split for wide tiles: four 4-warp groups each convert a quarter of every tile's columns (see the kernel)
   p.colsplit = (cs && BN > 128 && (BN / 4) % (d.out_f32 ? 32 : 64) == 0) ? 1 : 0;
-  if (p.colsplit) { p.n_acc = 2; p.n_grp = 4; p.lgw = 2; }
+  // ... and for 128-column tiles of layers with only a few tiles per CTA (the 20x20 / 40x40 maps; every layer of a
+  // single-frame call): with one group per tile the other three idle while one converts 128 columns alone (~2.9 us per tile
+  // in the timeline, the longest link of those layers' chains); split, each converts 32 columns (64-B staging rows)
+  static const int cs128_env = getenv("CC_COLSPLIT128") ? atoi(getenv("CC_COLSPLIT128")) : 3;   // max tiles per CTA; 0 = off
+  const int tiles_per_cta = (p.num_tiles + num_sms - 1) / num_sms;
+  const bool cs_narrow = cs && cs128_env > 0 && BN == 128 && level == 0 && tiles_per_cta <= cs128_env;
+  if (cs_narrow) p.colsplit = 1;
+  if (cs_narrow) { p.n_acc = 4; p.n_grp = 4; p.lgw = 2; }
+  else if (p.colsplit) { p.n_acc = 2; p.n_grp = 4; p.lgw = 2; }
   else if (BN > 128) { p.n_acc = 2; p.n_grp = 2; p.lgw = 3; }
   else { p.n_acc = level == 0 ? 4 : 2; p.n_grp = p.n_acc; p.lgw = 2; }
   int CH = (p.lgw == 2 || level >= 1) ? (d.out_f32 ? 32 : 64) : (d.out_f32 ? 64 : 128);
   if (CH > BN) CH = BN;
+  if (p.colsplit && CH > BN / 4) CH = BN / 4;
   p.CH = CH;
   static const int tmas_env = getenv("CC_TMASTORE") ? atoi(getenv("CC_TMASTORE")) : 1;
   static const int tmas64_env = getenv("CC_TMASTORE64") ? atoi(getenv("CC_TMASTORE64")) : 1;
   p.stg_lrow = 7;
-  p.tma_store = (tmas_env && (BN * es) % 128 == 0) ? 1 : 0;
-  if (!p.tma_store && tmas_env && tmas64_env && (BN * es) % 64 == 0) {   // narrow tiles (BN = 32 bf16, 16 fp32, ...): 64-B rows
+  const int wcols = p.colsplit ? BN / 4 : BN;      // columns one epilogue group stores per tile
+  p.tma_store = (tmas_env && (wcols * es) % 128 == 0) ? 1 : 0;
+  if (!p.tma_store && tmas_env && tmas64_env && (wcols * es) % 64 == 0) {   // narrow tiles (BN = 32 bf16, 16 fp32, ...): 64-B rows
     p.tma_store = 1;
     p.stg_lrow = 6;
   }
@@ -977,7 +988,9 @@ budget_again:
       // (BN = 128) the 3x3 128->128 convs ran at 57 % of their tensor time, and halving the bytes per CTA (pair multicast) did
       // not move them: the depth was the limit.  A halo buffer, in contrast, holds nine k-blocks of work, so two of them are
       // enough to prefetch one chunk ahead: weight stages are bought before the third halo buffer.
-      static const int bdepth_env = getenv("CC_B_INFLIGHT_KB") ? atoi(getenv("CC_B_INFLIGHT_KB")) : 80;
+      // (Measured again once the 10-pixel halo pitch had freed shared memory: 112 KB wanted is +0.7 % on the step over 80 KB —
+      // under load the latency is longer than the idle figure.)
+      static const int bdepth_env = getenv("CC_B_INFLIGHT_KB") ? atoi(getenv("CC_B_INFLIGHT_KB")) : 112;
       const int want = (bdepth_env * 1024 + b_bytes - 1) / b_bytes;
       S = 3;
       while (S < 8 && S < want && avail - (S + 1) * b_bytes >= 2 * p.halo_bytes) ++S;
