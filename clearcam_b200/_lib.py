@@ -44,6 +44,7 @@ _SIGS = {
     "cc_yolo_layer_output": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, ctypes.POINTER(_i), ctypes.POINTER(_i),
                                   ctypes.POINTER(_i), _vp]),
     "cc_detect_postprocess": (_i, [_vp, _i, _i, _i, _f, _i, _f, _f, _f, _f, _f, _vp, _vp]),
+    "cc_detect_pred_from_raw": (_i, [_vp, _i, _i, _i, _f, _vp, _vp]),
     "cc_detect_decode": (_i, [ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_i), ctypes.POINTER(_i), _i, _f,
                               _vp, _vp, _vp]),
     "cc_clip_create": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(_vp), ctypes.POINTER(ctypes.c_int64),

@@ -93,6 +93,45 @@ int decode_launch(const DecodeParams& p, cudaStream_t s) {
   return CC_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ head of postprocess
+// detection/yolov9.py:440-448 on a (B, 4 + nc, A) head output [xc, yc, w, h, class probabilities]: xywh -> xyxy, max /
+// first argmax over the classes, confidence threshold -> [B, A, 6].  thread == anchor: every one of the 4 + nc reads is
+// coalesced across the warp (the anchor is the fastest axis).  The model path never runs this (decode_kernel produces the
+// same six values straight from the logits); it serves the standalone `postprocess(output)` of the reference's API.
+__global__ void pred_from_raw_kernel(const float* __restrict__ raw, int B, int A, int nc, float conf_thr, float* __restrict__ pred) {
+  const long long total = static_cast<long long>(B) * A;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(idx / A), a = static_cast<int>(idx - static_cast<long long>(b) * A);
+    const float* r = raw + static_cast<long long>(b) * (4 + nc) * A + a;
+    const float xc = __ldg(r), yc = __ldg(r + A), w = __ldg(r + 2LL * A), h = __ldg(r + 3LL * A);
+    float best = __ldg(r + 4LL * A);
+    int besti = 0;
+    for (int c = 1; c < nc; ++c) {
+      const float v = __ldg(r + static_cast<long long>(4 + c) * A);
+      if (v > best) { best = v; besti = c; }     // first maximum wins ties (argmax)
+    }
+    float* o = pred + idx * 6;
+    o[0] = __fsub_rn(xc, __fdiv_rn(w, 2.0f));
+    o[1] = __fsub_rn(yc, __fdiv_rn(h, 2.0f));
+    o[2] = __fadd_rn(xc, __fdiv_rn(w, 2.0f));
+    o[3] = __fadd_rn(yc, __fdiv_rn(h, 2.0f));
+    o[4] = best >= conf_thr ? best : 0.f;
+    o[5] = static_cast<float>(besti);
+  }
+}
+
+int pred_from_raw_launch(const float* raw, int B, int A, int nc, float conf_thr, float* pred, cudaStream_t s) {
+  CC_REQUIRE(B >= 0 && A >= 0 && nc >= 1, "pred_from_raw: bad shape B=%d A=%d nc=%d", B, A, nc);
+  const long long total = static_cast<long long>(B) * A;
+  if (total == 0) return CC_OK;
+  long long blocks = (total + 127) / 128;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  pred_from_raw_kernel<<<static_cast<int>(blocks), 128, 0, s>>>(raw, B, A, nc, conf_thr, pred);
+  CC_CHECK_CUDA(cudaGetLastError());
+  return CC_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ postprocess
 static constexpr int kPostThreads = 1024;
 static constexpr int kMaxDet = 512;  // smem sized for max_det <= 512

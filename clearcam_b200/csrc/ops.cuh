@@ -110,6 +110,9 @@ struct DecodeParams {
 };
 int decode_launch(const DecodeParams& p, cudaStream_t s);
 
+// head of postprocess (detection/yolov9.py:440-448) on a [B, 4+nc, A] head output -> pred [B, A, 6]
+int pred_from_raw_launch(const float* raw, int B, int A, int nc, float conf_thr, float* pred, cudaStream_t s);
+
 // postprocess tail (detection/yolov9.py:449-458) + scale_boxes/clip_boxes (:406-421), one CTA per image.
 struct PostParams {
   const float* pred; int B, A; int max_det; float iou_thr;

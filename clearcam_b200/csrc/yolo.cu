@@ -1232,6 +1232,10 @@ int cc_detect_postprocess(const float* d_pred, int B, int A, int max_det, float 
   return postprocess_launch(p, static_cast<cudaStream_t>(stream));
 }
 
+int cc_detect_pred_from_raw(const float* d_raw, int B, int n_classes, int A, float conf_thr, float* d_pred, void* stream) {
+  return pred_from_raw_launch(d_raw, B, A, n_classes, conf_thr, d_pred, static_cast<cudaStream_t>(stream));
+}
+
 int cc_detect_decode(const float* const* d_box, const float* const* d_cls, const int* hs, const int* ws, int B,
                      float conf_thr, float* d_pred, float* d_raw, void* stream) {
   DecodeParams p{};

@@ -113,12 +113,10 @@ def postprocess(output, max_det=300, conf_threshold=0.25, iou_threshold=0.45):
     t = output.tensor if isinstance(output, DeviceResult) else output
     if not isinstance(t, torch.Tensor):
         t = torch.as_tensor(np.asarray(t))
-    t = t.to("cuda", torch.float32)
-    xc, yc, w, h, cls = t[:, 0], t[:, 1], t[:, 2], t[:, 3], t[:, 4:]
-    probs, ids = cls.max(1)
-    probs = torch.where(probs >= conf_threshold, probs, torch.zeros_like(probs))
-    pred = torch.stack([xc - w / 2, yc - h / 2, xc + w / 2, yc + h / 2, probs, ids.float()], 2).contiguous()
-    B, A = pred.shape[0], pred.shape[1]
+    t = t.to("cuda", torch.float32).contiguous()
+    B, C, A = t.shape
+    pred = torch.empty(B, A, 6, device="cuda", dtype=torch.float32)
+    check(lib().cc_detect_pred_from_raw(ptr(t), B, C - 4, A, conf_threshold, ptr(pred), stream_ptr()), "cc_detect_pred_from_raw")
     out = torch.empty(B, max_det, 6, device="cuda", dtype=torch.float32)
     check(lib().cc_detect_postprocess(ptr(pred), B, A, max_det, iou_threshold, 0, 0.0, 0.0, 1.0, 0.0, 0.0, ptr(out),
                                       stream_ptr()), "cc_detect_postprocess")

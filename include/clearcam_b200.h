@@ -115,6 +115,9 @@ int cc_yolo_layer_output(cc_yolo* h, int is_f32, int B, int Hf, int Wf, int res,
  * d_out [B,max_det,6] */
 int cc_detect_postprocess(const float* d_pred, int B, int A, int max_det, float iou_thr, int do_scale, float pad_x,
                           float pad_y, float gain, float clip_w, float clip_h, float* d_out, void* stream);
+/* head of the standalone postprocess(output) (detection/yolov9.py:440-448): d_raw [B, 4+n_classes, A] = xc, yc, w, h, class
+ * probabilities -> d_pred [B,A,6] = x1, y1, x2, y2, max probability (0 below conf_thr), first argmax */
+int cc_detect_pred_from_raw(const float* d_raw, int B, int n_classes, int A, float conf_thr, float* d_pred, void* stream);
 /* DDetect tail (detection/yolov9.py:209-219) + head of postprocess (:440-448): three scales of fp32 logits
  * d_box[i] [B,h,w,64], d_cls[i] [B,h,w,80] (strides 8,16,32) -> d_pred [B,A,6], optional d_raw [B,84,A] */
 int cc_detect_decode(const float* const* d_box, const float* const* d_cls, const int* hs, const int* ws, int B,
